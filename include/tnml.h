@@ -1,0 +1,144 @@
+/* tnml.h -- C ABI of the B200-native MPS-classifier sweep (libtnml.so).
+ *
+ * The reference (francescovidaich964/TensorNetworkForML) is pure Python + NumPy and has NO FFI of its own
+ * (SURVEY.md section 2.1 / 8b): its boundary is the Python API of Network_class.py (NC), Tensor_class.py (TC)
+ * and custom_linalg_tools.py (CLT).  This header is the C ABI that sits UNDER that Python API; every entry
+ * point names the reference code it replaces (file:line under /root/reference/TensorNetwork).
+ *
+ * Conventions
+ *  - plain C types only; all data pointers are DEVICE pointers unless a parameter says "host".
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and keeps no
+ *    global state: the caller owns every buffer, including workspaces sized by the *_workspace_bytes queries.
+ *  - return value: 0 = ok; TNML_ERR_* (< 0) for argument errors; -(1000 + cudaError_t) for CUDA launch errors.
+ *  - dtype: TNML_F64 is the parity path (FP64, DMMA tensor cores).  TNML_F32 is declared for the FP32/TF32
+ *    variant and currently returns TNML_ERR_UNSUPPORTED.
+ *
+ * Device layouts ("canonical"), all row-major, d = 2 physical components:
+ *    phi   [S][Ns][2]        feature-mapped input, site-major
+ *    env   [Ns][D]           per-sample environment (left env of sites < p, or right env of sites >= p)
+ *    site  [Dl][2][Dr]       plain site tensor          (a, sigma, c)
+ *    label site, right sweep [Dl][2][L][Dr]  (a, sigma, l, c);  left sweep [Dl][L][2][Dr]  (a, l, sigma, c)
+ *    B     [Dl][2][L][2][Dr] bond tensor                (a, sigma, l, tau, c)
+ *    f, q  [Ns][L], [Ns][L][4]   outputs; q = lossder * phi_p(sigma) * phi_q(tau)
+ */
+#ifndef TNML_H
+#define TNML_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* tnml_stream_t; /* cudaStream_t */
+
+enum { TNML_F64 = 0, TNML_F32 = 1 };
+enum { TNML_ACT_LINEAR = 0, TNML_ACT_SIGMOID = 1, TNML_ACT_SOFTMAX = 2 };          /* NC:127 */
+enum { TNML_LOSS_MSE = 0, TNML_LOSS_CROSS_ENTROPY = 1, TNML_LOSS_FULL_CROSS_ENT = 2 }; /* NC:132 */
+enum {
+  TNML_OK = 0,
+  TNML_ERR_INVALID = -1,     /* bad dimension / null pointer / enum out of range */
+  TNML_ERR_UNSUPPORTED = -2, /* dtype or size not implemented on this build */
+  TNML_ERR_WORKSPACE = -3    /* workspace too small */
+};
+
+int tnml_version(void);
+/* Human-readable text for a return code (static storage). */
+const char* tnml_error_string(int code);
+
+/* ---- a1: feature map + input packing ------------------------------------------------------------
+ * tnml_feature_map   : phi[s][b][:] = [sin(pi x[b][s]/2), cos(pi x[b][s]/2)]  (sin first)   DG:165-167, NC:152-155
+ * tnml_pack_features : X[b][s][:] (the (Ns,S,2) array the reference API takes) -> phi[s][b][:]   NC:222-225 */
+int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream);
+int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a5/a10: environment advance ------------------------------------------------------------------
+ * out[b][m] = sum_sigma phi_p[b][sigma] * sum_k E[b][k] * W[k][sigma][m]
+ * W is the site tensor seen from the side the environment comes from: right-moving (left env) W = site
+ * [Dl][2][Dr] as stored; left-moving (right env) W[c][sigma][a] = site[a][sigma][c] (tnml_site_transpose).
+ * Replaces contract(As[i],TX[i]) + contract(cum, A_TX) : NC:227-255, NC:637-642, NC:669-674 (CLT:81-84). */
+int tnml_env_advance(const void* E, const void* phi_p, const void* W, void* out, int64_t Ns, int32_t K, int32_t M,
+                     int32_t dtype, tnml_stream_t stream);
+/* Wt[c][sigma][a] = site[a][sigma][c] */
+int tnml_site_transpose(const void* site, void* Wt, int32_t Dl, int32_t Dr, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a5: last contraction of forward ----------------------------------------------------------------
+ * f[b][l] = sum L[b][a] phi_p[b][sigma] A[a][sigma][l][c] R[b][c]   (label site in right-sweep layout)
+ * NC:242 / NC:255 (r_cum_contraction[0] / l_cum_contraction[-1]). */
+int tnml_site_predict(const void* Lenv, const void* phi_p, const void* A_label, const void* Renv, void* f, int64_t Ns,
+                      int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a11/a12/a7: activation, loss derivative, metrics ------------------------------------------------
+ * fa = act(f / T) (NC:767-796, softmax NOT max-stabilised), g = dloss(fa, onehot(y)) (NC:800-835),
+ * q[b][l][2*sigma+tau] = g[b][l] * phi_p[b][sigma] * phi_q[b][tau]   (operand of the gradient GEMM)
+ * pp[b][2*sigma+tau]   = phi_p[b][sigma] * phi_q[b][tau]             (operand of the projection epilogue)
+ * metrics[0] = number of samples with argmax(fa) == y, metrics[1] = sum |onehot(y) - fa|   (NC:697-702)
+ * The two sums are reduced in a fixed order (deterministic).  ws: tnml_act_lossder_workspace_bytes(Ns). */
+int64_t tnml_act_lossder_workspace_bytes(int64_t Ns);
+int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const void* phi_q, void* q, void* pp,
+                     void* metrics, void* ws, int64_t Ns, int32_t L, int32_t act, int32_t loss, double T,
+                     int32_t dtype, tnml_stream_t stream);
+
+/* ---- a10: gradient, a K = Ns tensor-core reduction ---------------------------------------------------
+ * dB[a][sigma][l][tau][c] = sum_b q[b][l][sigma,tau] L[b][a] R[b][c]          NC:625-646 + NC:710
+ * Split-K over samples with a static decomposition and a fixed-order second stage => bitwise reproducible.
+ * ws: tnml_grad_workspace_bytes(...). */
+int64_t tnml_grad_workspace_bytes(int64_t Ns, int32_t Dl, int32_t Dr, int32_t L);
+int tnml_grad(const void* q, const void* Lenv, const void* Renv, void* dB, void* ws, int64_t Ns, int32_t Dl, int32_t Dr,
+              int32_t L, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a9: bond tensor formation and projection ----------------------------------------------------------
+ * tnml_gemm: C = alpha * op(A) * op(B) + beta * C, row-major, used for B = A_p . A_q (NC:484), the L2 term and the
+ * norm environments (NC:966-1179); transX != 0 means the stored matrix is the transpose.
+ * tnml_project: f[b][l] = sum B[a][sigma][l][tau][c] L[b][a] pp[b][sigma,tau] R[b][c]     NC:494-523 */
+int tnml_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, double alpha, const void* A, int32_t lda,
+              const void* B, int32_t ldb, double beta, void* C, int32_t ldc, int32_t dtype, tnml_stream_t stream);
+int64_t tnml_project_workspace_bytes(int64_t Ns, int32_t Dl, int32_t Dr, int32_t L);
+int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Renv, void* f, void* ws, int64_t Ns,
+                 int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a10/a14: regularisation, clipping, update --------------------------------------------------------
+ * reg  = L2_flag ? 2 wd * (E_L . B . E_R) : wd * B                     NC:728-734, NC:1129-1177
+ * dB  -= reg ; if sum|dB| > sum|B| : dB /= (sum|dB| / sum|B|) ; B' = B + lr * dB        NC:755-761
+ * stats[0..5] = { sum|B|, sum|dB| (after reg, before clip), wd*<B, E_L B E_R> (0 if !L2_flag), clipped?,
+ *                 mean|B|, mean|dB| }                                     (NC:741-747 debug history)
+ * EL [Dl][Dl], ER [Dr][Dr] norm environments (ignored when !L2_flag).  Bnew may alias neither B nor dB. */
+int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L);
+int tnml_bond_update(const void* B, const void* dB, const void* EL, const void* ER, void* Bnew, void* stats, void* ws,
+                     int32_t Dl, int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag, int32_t dtype,
+                     tnml_stream_t stream);
+
+/* ---- a14: norm environments ----------------------------------------------------------------------------
+ * right-moving: Eout[m][m'] = sum_{a,a',s} Ein[a][a'] A[a][s][m] A[a'][s][m']          NC:1004-1029
+ * left-moving : Eout[a][a'] = sum_{c,c',s} A[a][s][c] A[a'][s][c'] Ein[c][c']          NC:1035-1061
+ * ws: 2*Dl*Dr elements. */
+int tnml_norm_env_step(const void* Ein, const void* site, void* Eout, void* ws, int32_t Dl, int32_t Dr,
+                       int32_t left_moving, int32_t dtype, tnml_stream_t stream);
+
+/* ---- a13: SVD split by one-sided Jacobi -----------------------------------------------------------------
+ * Mx = B' viewed as R x C (right sweep: R = 2 Dl, C = 2 L Dr; left sweep: R = 2 Dl L, C = 2 Dr)   NC:528-560
+ * U S Vh = svd(Mx); keep m; left site = U[:, :m] sqrt(S), right site = sqrt(S) Vh[:m]     NC:887-925, NC:947-960
+ * Implementation: Gram matrix of the short side, one-sided (Hestenes) Jacobi on it inside one CTA, a second
+ * pass on the rotated matrix to restore full accuracy for small singular values, then the two factors are
+ * written straight into the destination site layouts:
+ *   right sweep: site_p[a][s][m] (plain),      site_q[m][tau][l][c] (label site, right-sweep layout)
+ *   left  sweep: site_p[a][l][s][m] (label site, left-sweep layout), site_q[m][tau][c] (plain)
+ * svals receives all min(R, C) singular values, descending.  m is chosen by the caller (truncation rule). */
+int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
+int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
+                   int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream);
+
+/* ---- label-site layout change between sweep directions: [a][s][l][c] <-> [a][l][s][c] ------------------- */
+int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32_t Dr, int32_t L, int32_t to_left_layout,
+                         int32_t dtype, tnml_stream_t stream);
+
+/* ---- a3: generic named-axis pair contraction (CLT:10-87) -------------------------------------------------
+ * out[u1][u2][c] = sum_k T1[u1][c][k] * T2[u2][c][k]   (operands already permuted to (unique, common, contracted)
+ * order, which is what CLT:51-75 does before the broadcast multiply of CLT:81 and the sums of CLT:82-84). */
+int tnml_contract(const void* T1, const void* T2, void* out, int64_t U1, int64_t U2, int64_t Cc, int64_t Kc,
+                  int32_t dtype, tnml_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNML_H */

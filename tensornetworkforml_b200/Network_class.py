@@ -1,0 +1,285 @@
+"""MPS classifier with sweeping (DMRG-style) training: drop-in for the reference's ``Network`` (NC:10-1179).
+
+Same constructor, methods, attributes and pickle layout as the reference; the arithmetic runs device-resident on a
+B200 through libtnml.so (see ``engine.SweepEngine``).  Additive keyword-only extensions:
+
+  truncation='reference' | 'fixed', max_bond=D   bond kept by the SVD split.  'reference' is the rule of NC:898-910 /
+                                                 NC:933-945 (copies the left bond, so interior bonds collapse to 2 and
+                                                 L>2 cannot finish a sweep -- SURVEY.md section 0.2); 'fixed' keeps
+                                                 min(len(S), max_bond) and cuts both factors.
+  device, process_group                          CUDA device; torch.distributed group for sample sharding (each rank
+                                                 feeds its own shard of the batch, dB and the metrics are all-reduced).
+  svd_refine                                     second Jacobi pass (default on; full accuracy for small sing. values)
+
+There is no CPU fallback: without a CUDA device or without libtnml.so the compute methods raise.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .Tensor_class import Tensor
+
+new = np.newaxis
+
+_ACTS = ['linear', 'sigmoid', 'softmax']
+_LOSSES = ['MSE', 'cross_entropy', 'full_cross_ent']
+
+
+def _named_to_canonical(T, p):
+    """Reference-style site Tensor (any axis order, names 'left','right','d<p>','l') -> (Dl,2,[L,]Dr) array."""
+    names = [str(n) for n in T.axes_names]
+    want = [w for w in ("left", "d%d" % p, "l", "right") if w in names]
+    arr = np.transpose(np.asarray(T.elem, dtype=np.float64), [names.index(w) for w in want])
+    if "left" not in names:
+        arr = arr[new, ...]
+    if "right" not in names:
+        arr = arr[..., new]
+    return np.ascontiguousarray(arr)
+
+
+def _canonical_to_named(A, p, S, is_label):
+    """(Dl,2,[L,]Dr) array -> Tensor with the reference's axis names; the dummy edge bonds are dropped."""
+    names = ["left", "d%d" % p] + (["l"] if is_label else []) + ["right"]
+    if p == S - 1:
+        A, names = A[..., 0], names[:-1]
+    if p == 0:
+        A, names = A[0], names[1:]
+    return Tensor(elem=np.array(A, copy=True), axes_names=names)
+
+
+class Network():
+    """Matrix Product State classifier (see the reference docstring NC:11-82 for the attribute list)."""
+
+    def __init__(self, N, M, D=2, L=10, T=0.1, normalize=False, calibration_X=None, act_fn='linear',
+                 loss_fn='cross_entropy', check=False, *, truncation='reference', max_bond=None, device=None,
+                 process_group=None, svd_refine=True):
+        self.N, self.D, self.L, self.M, self.T = N, D, L, M, T
+        if D != 2:
+            raise NotImplementedError("the device kernels are written for the 2-component feature map (D=2)")
+        assert act_fn in _ACTS, "Please select an activation function between 'linear', 'sigmoid', 'softmax'"
+        assert loss_fn in _LOSSES, "Please select a loss function between 'MSE', 'cross_entropy', 'full_cross_ent'"
+        self.act_fn, self.loss_fn = act_fn, loss_fn
+        self.l_pos = 0
+        self._opts = dict(truncation=truncation, max_bond=max_bond, svd_refine=bool(svd_refine))
+        self._device, self._group = device, process_group
+        self._eng = None
+        self._host_As = None          # list[Tensor]; authoritative when _host_fresh
+        self._host_fresh = True
+        self._last_f = None
+
+        # weights: same RNG calls, order and shapes as NC:145-148 / NC:186-189 (Tensor draws np.random.random)
+        scale = float(M) * 0.5 * 0.64 * D if normalize else 1.
+        if normalize:
+            print('Normalizing weights...')
+            print('Scaling factor: %.2f' % scale)
+        As = [Tensor(shape=[L, M, D], axes_names=['l', 'right', 'd0'], scale=scale)]
+        for i in range(1, N - 1):
+            As.append(Tensor(shape=[M, M, D], axes_names=['left', 'right', 'd' + str(i)], scale=scale))
+        As.append(Tensor(shape=[M, D], axes_names=['left', 'd' + str(N - 1)], scale=scale))
+        self._host_As = As
+
+        if normalize:
+            if calibration_X is None:
+                X = np.random.random((16, N))                                             # NC:157-159
+                X = np.stack((np.sin(np.pi * X / 2), np.cos(np.pi * X / 2)), axis=-1)
+            else:
+                X = calibration_X
+            B = X.shape[0]
+            print('\nCalibrating weights on dataset...')
+            f = self.forward(X)
+            f_max = self._abs_max(f)
+            F2 = f_max ** (1. / N)                                                        # NC:170
+            if check:
+                print('f_max for random input of %d samples : ' % B, f_max)
+            print("Rescaling factor for calibration: ", F2)
+            self._engine().scale_sites(F2)                                                # NC:175-176
+            self._host_fresh = False
+            self.calibration_factor = F2
+            f = self.forward(X)                                                           # NC:179
+            if check:
+                print('f_max for random input of %d samples (after): ' % B, self._abs_max(f))
+
+    # ------------------------------------------------------------------ device plumbing
+    def _abs_max(self, f):
+        m = float(np.abs(f.elem).max())
+        eng = self._eng
+        if eng is not None and eng.world > 1:
+            import torch
+            t = torch.tensor([m], dtype=torch.float64, device=eng.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=eng.group)
+            m = float(t.item())
+        return m
+
+    def _engine(self):
+        if self._eng is None:
+            from .engine import SweepEngine
+            self._eng = SweepEngine(self.N, self.L, self.T, self.act_fn, self.loss_fn,
+                                    rule=self._opts["truncation"], max_bond=self._opts["max_bond"],
+                                    device=self._device, group=self._group, svd_refine=self._opts["svd_refine"])
+            self._upload()
+        elif self._host_fresh and self._host_dirty:
+            self._upload()
+        return self._eng
+
+    _host_dirty = True
+
+    def _upload(self):
+        sites = [_named_to_canonical(T, p) for p, T in enumerate(self._host_As)]
+        lab = sites[self.l_pos]
+        if lab.ndim != 4:
+            raise ValueError("site %d should carry the label axis 'l' (l_pos=%d)" % (self.l_pos, self.l_pos))
+        self._eng.set_sites(sites, self.l_pos)
+        self._host_dirty = False
+
+    @property
+    def As(self):
+        """Site tensors as reference-style named Tensors (downloaded from the device when it holds newer values)."""
+        if not self._host_fresh:
+            eng = self._eng
+            sites = eng.get_sites()
+            self._host_As = [_canonical_to_named(A, p, self.N, p == eng.l_pos) for p, A in enumerate(sites)]
+            self._host_fresh, self._host_dirty = True, False
+        return self._host_As
+
+    @As.setter
+    def As(self, value):
+        self._host_As = list(value)
+        self._host_fresh, self._host_dirty = True, True
+
+    def sync_to_device(self):
+        """Call after editing ``net.As[i].elem`` in place on the host."""
+        self._host_fresh, self._host_dirty = True, True
+        self._engine()
+
+    # ------------------------------------------------------------------ forward (NC:195-258)
+    def forward(self, X):
+        """Predictions (no activation) for X of shape (batch, N, D); returns a Tensor with axes ('l','b')."""
+        assert self.N == X.shape[1], "The 1 dimension of the input data must be the flattened number of pixels"
+        eng = self._engine()
+        eng.load_input(X)
+        f_dev = eng.forward()
+        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        self._last_f = out
+        return out
+
+    # ------------------------------------------------------------------ train (NC:261-350)
+    def train(self, train_loader, val_loader, lr, n_epochs=10, weight_dec=0.001, L2_flag=True, debug=False):
+        val_acc, var_hist = [], []
+        print("\n --- TRAINING PROCEDURE ---")
+        for epoch in range(n_epochs):
+            epoch_train_acc = np.zeros(len(train_loader))
+            var_hist.append([[] for _ in range(7)] if debug else [[], []])
+            for i, data in enumerate(train_loader, 0):
+                x = np.array([s[0] for s in data])
+                y = np.array([s[1] for s in data])
+                f = self.forward(x)
+                epoch_train_acc[i] = self.accuracy(x, y, f)          # accuracy before the batch optimisation
+                left_dir = (self.l_pos == self.N - 1)
+                f = self.sweep(x, y, f, lr, weight_dec, L2_flag=L2_flag, left_dir=left_dir, var_hist=var_hist[epoch],
+                               debug=debug)
+                print('\r' + "Epoch %d/%d - train accuracy : %.4f - completed : %.2f " %
+                      (epoch, n_epochs, epoch_train_acc[i], (i + 1) * 100 / len(train_loader)) + '%', end=' ')
+            epoch_val_acc = np.zeros(len(val_loader))
+            for i, data in enumerate(val_loader, 0):
+                x = np.array([s[0] for s in data])
+                y = np.array([s[1] for s in data])
+                epoch_val_acc[i] = self.accuracy(x, y)
+            val_acc.append(epoch_val_acc.mean())
+            print('\r' + "Epoch %d/%d - train accuracy : %.4f - val accuracy: %.4f" %
+                  (epoch, n_epochs, epoch_train_acc.mean(), val_acc[-1]))
+        return val_acc, np.array(var_hist)
+
+    # ------------------------------------------------------------------ accuracy (NC:354-380)
+    def accuracy(self, X, y, f=None):
+        if f is None:
+            f = self.forward(X)
+        y_pred = np.argmax(f.elem, axis=0)
+        errors = (np.asarray(y) != y_pred).sum()
+        return (len(y_pred) - errors) / len(y_pred)
+
+    # ------------------------------------------------------------------ sweep (NC:384-436)
+    def sweep(self, X, y, f, lr, weight_dec, L2_flag=True, left_dir=False, var_hist=None, debug=False):
+        """One optimisation sweep over the batch loaded by the last ``forward`` (like the reference, X itself is not
+        re-read).  Runs entirely on the device; per-step metrics are fetched once at the end."""
+        eng = self._engine()
+        if eng.phi is None:
+            raise Exception("call forward(X) before sweep: the environments of the batch are built there")
+        self._push_f(f)
+        y = np.asarray(y)
+        eng.begin_sweep(y, left_dir, L2_flag)
+        f_dev = None
+        for _ in range(self.N - 1):
+            f_dev = eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
+        self._after_steps(var_hist, debug, L2_flag)
+        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        self._last_f = out
+        return out
+
+    def _push_f(self, f):
+        """Use the caller's f if it is not the Tensor we returned last (then the device copy is already current)."""
+        eng = self._eng
+        if f is not None and f is not self._last_f:
+            import torch
+            host = np.ascontiguousarray(np.asarray(f.elem, dtype=np.float64).T)
+            eng.f_buf[eng.f_cur].copy_(torch.from_numpy(host.reshape(-1)))
+
+    def _after_steps(self, var_hist, debug, L2_flag):
+        eng = self._eng
+        self.l_pos = eng.l_pos
+        self._host_fresh = False
+        h = eng.history()
+        self.last_history = h
+        if var_hist is not None:
+            for i in range(len(h["acc"])):
+                if debug:                                               # NC:741-747
+                    if not L2_flag:
+                        raise NameError("name 'L2_loss_term' is not defined")   # the reference's latent bug, NC:746
+                    var_hist[0].append(h["stats"][i, 4])
+                    var_hist[1].append(h["stats"][i, 5])
+                    var_hist[2].append(h["acc"][i])
+                    var_hist[3].append(np.nan)
+                    var_hist[4].append(h["mae"][i])
+                    var_hist[5].append(h["stats"][i, 2])
+                    var_hist[6].append(np.nan)
+                else:                                                   # NC:749-750
+                    var_hist[0].append(h["acc"][i])
+                    var_hist[1].append(h["mae"][i])
+
+    def sweep_step(self, f, y, lr, batch_size, weight_dec, L2_flag=True, left_dir=False, var_hist=None, debug=False):
+        """One bond update (NC:440-573).  ``y`` is the one-hot target (L, batch) like in the reference."""
+        eng = self._engine()
+        self._push_f(f)
+        y = np.asarray(y)
+        labels = np.argmax(y, axis=0) if y.ndim == 2 else y
+        first = (self.l_pos == (self.N - 1 if left_dir else 0))
+        if first or eng.hist is None:
+            eng.begin_sweep(labels, left_dir, L2_flag)
+        else:                                   # keep the norm-environment stacks, restart the per-call record
+            eng.set_labels(labels)
+            eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+        f_dev = eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
+        self._after_steps(var_hist, debug, L2_flag)
+        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        self._last_f = out
+        return out
+
+    # ------------------------------------------------------------------ pickle layout
+    def __getstate__(self):
+        As = self.As
+        state = dict(N=self.N, D=self.D, L=self.L, M=self.M, T=self.T, As=As, l_pos=self.l_pos,
+                     act_fn=self.act_fn, loss_fn=self.loss_fn, TX=[], r_cum_contraction=None,
+                     l_cum_contraction=None, tnml_options=dict(self._opts))
+        return state
+
+    def __setstate__(self, state):
+        state = dict(state)
+        self._opts = state.pop("tnml_options", dict(truncation='reference', max_bond=None, svd_refine=True))
+        self._host_As = state.pop("As")
+        for k in ("TX", "r_cum_contraction", "l_cum_contraction"):
+            state.pop(k, None)
+        self.__dict__.update(state)
+        self._device = self._group = self._eng = self._last_f = None
+        self._host_fresh, self._host_dirty = True, True
+
+
+Network.__module__ = "Network_class"     # pickles stay interchangeable with the reference

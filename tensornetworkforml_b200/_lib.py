@@ -1,0 +1,78 @@
+"""ctypes binding of libtnml.so (the C ABI declared in include/tnml.h).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtnml.so")
+
+F64, F32 = 0, 1
+ACT = {"linear": 0, "sigmoid": 1, "softmax": 2}
+LOSS = {"MSE": 0, "cross_entropy": 1, "full_cross_ent": 2}
+
+# every symbol include/tnml.h declares: name -> (restype, argtypes)
+_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+SIGNATURES = {
+    "tnml_version": (C.c_int, []),
+    "tnml_error_string": (C.c_char_p, [C.c_int]),
+    "tnml_feature_map": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "tnml_pack_features": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "tnml_env_advance": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
+    "tnml_site_transpose": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "tnml_site_predict": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_act_lossder_workspace_bytes": (_i64, [_i64]),
+    "tnml_act_lossder": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f64, _i32, _vp]),
+    "tnml_grad_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "tnml_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _i32, _f64, _vp, _i32, _i32, _vp]),
+    "tnml_project_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "tnml_project": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_bond_update_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "tnml_bond_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _vp]),
+    "tnml_norm_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_svd_split_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "tnml_svd_split": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_label_site_swap": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_contract": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
+}
+
+
+class TnmlError(RuntimeError):
+    pass
+
+
+_lib = None
+launches = 0   # number of C-ABI compute calls issued (each enqueues >= 1 kernel); read by bench.py
+
+
+def lib():
+    """Load libtnml.so once.  Raises ImportError loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libtnml.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().tnml_error_string(rc).decode()
+        raise TnmlError("%s failed: %s (code %d)" % (what or "tnml call", msg, rc))
+
+
+def call(name: str, *args):
+    """Invoke a compute entry point, raising TnmlError on a non-zero return code."""
+    global launches
+    launches += 1
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,217 @@
+// Batch-independent pieces of a bond update: small GEMMs (bond-tensor formation, norm environments, L2 term),
+// regularisation + clipping + update.   NC:484, NC:728-761, NC:966-1179
+#include "common.cuh"
+
+namespace tnml {
+
+// ---------------------------------------------------------------------------------------------------
+// Row-major C = alpha * op(A) . op(B) + beta * C.  64x64 tile, 256 threads, 4x4 register tile (plain DFMA:
+// these products are at most tens of MFLOP and never leave L2).
+// TA: A stored K x M (element (m,k) at k*lda + m).  TB: B stored N x K (element (k,n) at n*ldb + k).
+// ---------------------------------------------------------------------------------------------------
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
+                                              const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
+                                              int ldc) {
+  __shared__ double As[16][65];
+  __shared__ double Bs[16][65];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = tid + 256 * i;
+      int m, k;
+      if (TA) { m = e & 63; k = e >> 6; } else { k = e & 15; m = e >> 4; }
+      double v = 0.0;
+      if (m0 + m < M && k0 + k < K) v = TA ? A[(size_t)(k0 + k) * lda + m0 + m] : A[(size_t)(m0 + m) * lda + k0 + k];
+      As[k][m] = v;
+      int n, kk;
+      if (TB) { kk = e & 15; n = e >> 4; } else { n = e & 63; kk = e >> 6; }
+      double w = 0.0;
+      if (n0 + n < N && k0 + kk < K) w = TB ? B[(size_t)(n0 + n) * ldb + k0 + kk] : B[(size_t)(k0 + kk) * ldb + n0 + n];
+      Bs[kk][n] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      double* c = C + (size_t)m * ldc + n;
+      *c = (beta == 0.0) ? alpha * acc[i][j] : alpha * acc[i][j] + beta * (*c);
+    }
+  }
+}
+
+static int launch_gemm(int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                       int ldb, double beta, double* C, int ldc, cudaStream_t st) {
+  dim3 grid(tnml_cdiv(N, 64), tnml_cdiv(M, 64));
+  if (!tA && !tB) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (tA && !tB) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else if (!tA && tB) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  return tnml_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// bond update, stage 1: d = dB - reg, block partial sums of |B|, |d|, <B, G>
+// ---------------------------------------------------------------------------------------------------
+constexpr int BU_THREADS = 256;
+
+__global__ void __launch_bounds__(BU_THREADS) k_bu_partial(const double* __restrict__ B, const double* __restrict__ dB,
+                                                          const double* __restrict__ G, double* __restrict__ D,
+                                                          double* __restrict__ partial, int n, double wd, int L2_flag) {
+  __shared__ double red[3][BU_THREADS];
+  int e = blockIdx.x * BU_THREADS + threadIdx.x;
+  double sb = 0.0, sd = 0.0, sg = 0.0;
+  if (e < n) {
+    double b = B[e];
+    double reg, gg = 0.0;
+    if (L2_flag) { gg = G[e]; reg = 2 * wd * gg; }  // NC:1176
+    else reg = wd * b;                                // NC:733
+    double d = dB[e] - reg;                          // NC:730 / NC:734
+    D[e] = d;
+    sb = fabs(b); sd = fabs(d); sg = b * gg;
+  }
+  red[0][threadIdx.x] = sb; red[1][threadIdx.x] = sd; red[2][threadIdx.x] = sg;
+  __syncthreads();
+  for (int s = BU_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[3 * blockIdx.x] = red[0][0];
+    partial[3 * blockIdx.x + 1] = red[1][0];
+    partial[3 * blockIdx.x + 2] = red[2][0];
+  }
+}
+
+// stage 2: every block re-reduces the partials in the same fixed order, then clips and updates its slice
+__global__ void __launch_bounds__(BU_THREADS) k_bu_apply(const double* __restrict__ B, const double* __restrict__ D,
+                                                        const double* __restrict__ partial, int nblocks,
+                                                        double* __restrict__ Bnew, double* __restrict__ stats, int n,
+                                                        double lr, double wd) {
+  __shared__ double red[3][BU_THREADS];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += BU_THREADS) {
+    s0 += partial[3 * i]; s1 += partial[3 * i + 1]; s2 += partial[3 * i + 2];
+  }
+  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int s = BU_THREADS / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  const double sumB = red[0][0], sumD = red[1][0], l2 = red[2][0];
+  const bool clip = sumD > sumB;  // NC:756
+  const double ratio = clip ? sumD / sumB : 1.0;
+  int e = blockIdx.x * BU_THREADS + threadIdx.x;
+  if (e < n) {
+    double d = D[e];
+    if (clip) d = d / ratio;  // NC:757 (division by the ratio, like the reference)
+    d = d * lr;               // NC:760
+    Bnew[e] = B[e] + d;       // NC:761
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    stats[0] = sumB; stats[1] = sumD; stats[2] = wd * l2; stats[3] = clip ? 1.0 : 0.0;
+    stats[4] = sumB / n; stats[5] = sumD / n;
+  }
+}
+
+}  // namespace tnml
+
+using namespace tnml;
+
+extern "C" int tnml_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, double alpha, const void* A,
+                         int32_t lda, const void* B, int32_t ldb, double beta, void* C, int32_t ldc, int32_t dtype,
+                         tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && lda > 0 && ldb > 0 && ldc > 0);
+  return launch_gemm(transA, transB, M, N, K, alpha, (const double*)A, lda, (const double*)B, ldb, beta, (double*)C, ldc,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L) {
+  int64_t n = (int64_t)Dl * 4 * L * Dr;
+  return (3 * n + 3 * (int64_t)tnml_cdiv(n, BU_THREADS)) * 8;
+}
+
+extern "C" int tnml_bond_update(const void* B, const void* dB, const void* EL, const void* ER, void* Bnew, void* stats,
+                                void* ws, int32_t Dl, int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag,
+                                int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(B && dB && Bnew && stats && ws && Dl > 0 && Dr > 0 && L > 0);
+  TNML_REQUIRE(Bnew != B && Bnew != dB);
+  if (L2_flag) TNML_REQUIRE(EL && ER);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = Dl * 4 * L * Dr;
+  double* T1 = (double*)ws;
+  double* G = T1 + n;
+  double* D = G + n;
+  double* partial = D + n;
+  if (L2_flag) {
+    // T1[a'][(s,l,t,c)] = sum_a EL[a'][a] B[a][...] ; G[(a,s,l,t)][c'] = sum_c T1[...][c] ER[c][c']     NC:1129-1135
+    int rc = launch_gemm(0, 0, Dl, 4 * L * Dr, Dl, 1.0, (const double*)EL, Dl, (const double*)B, 4 * L * Dr, 0.0, T1,
+                         4 * L * Dr, st);
+    if (rc) return rc;
+    rc = launch_gemm(0, 0, Dl * 4 * L, Dr, Dr, 1.0, T1, Dr, (const double*)ER, Dr, 0.0, G, Dr, st);
+    if (rc) return rc;
+  }
+  const int nb = tnml_cdiv(n, BU_THREADS);
+  k_bu_partial<<<nb, BU_THREADS, 0, st>>>((const double*)B, (const double*)dB, G, D, partial, n, wd, L2_flag);
+  k_bu_apply<<<nb, BU_THREADS, 0, st>>>((const double*)B, D, partial, nb, (double*)Bnew, (double*)stats, n, lr, wd);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_norm_env_step(const void* Ein, const void* site, void* Eout, void* ws, int32_t Dl, int32_t Dr,
+                                  int32_t left_moving, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(Ein && site && Eout && ws && Dl > 0 && Dr > 0 && Ein != Eout);
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* E = (const double*)Ein;
+  const double* A = (const double*)site;
+  double* T = (double*)ws;
+  int rc;
+  if (!left_moving) {
+    // T[a'][(s,m)] = sum_a E[a'][a] A[a][(s,m)] ; Eout[m][m'] = sum_{(a',s)} A[(a',s)][m] T[(a',s)][m']
+    rc = launch_gemm(0, 0, Dl, 2 * Dr, Dl, 1.0, E, Dl, A, 2 * Dr, 0.0, T, 2 * Dr, st);
+    if (rc) return rc;
+    rc = launch_gemm(1, 0, Dr, Dr, 2 * Dl, 1.0, A, Dr, T, Dr, 0.0, (double*)Eout, Dr, st);
+  } else {
+    // T[(a,s)][c'] = sum_c A[(a,s)][c] E[c][c'] ; Eout[a][a'] = sum_{(s,c)} A[a][(s,c)] T[a'][(s,c)]
+    rc = launch_gemm(0, 0, 2 * Dl, Dr, Dr, 1.0, A, Dr, E, Dr, 0.0, T, Dr, st);
+    if (rc) return rc;
+    rc = launch_gemm(0, 1, Dl, Dl, 2 * Dr, 1.0, A, 2 * Dr, T, 2 * Dr, 0.0, (double*)Eout, Dl, st);
+  }
+  return rc;
+}

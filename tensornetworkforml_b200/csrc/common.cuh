@@ -1,0 +1,99 @@
+// Shared device/host helpers for libtnml (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tnml.h"
+
+#define TNML_CUDA_ERR(e) (-(1000 + (int)(e)))
+
+// Return the launch status of the kernel(s) just enqueued (no synchronisation).
+static inline int tnml_launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? TNML_OK : TNML_CUDA_ERR(e);
+}
+
+#define TNML_REQUIRE(cond) \
+  do {                     \
+    if (!(cond)) return TNML_ERR_INVALID; \
+  } while (0)
+
+#define TNML_F64_ONLY(dtype)                          \
+  do {                                                \
+    if ((dtype) == TNML_F32) return TNML_ERR_UNSUPPORTED; \
+    if ((dtype) != TNML_F64) return TNML_ERR_INVALID;     \
+  } while (0)
+
+static inline int64_t tnml_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline int tnml_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+namespace tnml {
+
+constexpr int kNumSMs = 148;  // B200
+
+// ---- FP64 tensor-core MMA (SASS DMMA.8x8x4) ----------------------------------------------------------
+// A 8x4 row-major : lane holds A[lane>>2][lane&3]
+// B 4x8 col-major : lane holds B[lane&3][lane>>2]
+// C 8x8           : lane holds C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// ---- cp.async (LDGSTS) 8-byte copy with zero fill when !valid ---------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, bool valid) {
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+  unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+// ---- TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS UBLKCP) ----------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(a),
+      "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// bytes must be a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace tnml

@@ -1,0 +1,48 @@
+// Generic named-axis pair contraction (the arithmetic of CLT:10-87) and library-level entry points.
+#include "common.cuh"
+
+namespace tnml {
+
+// out[u1][u2][c] = sum_k T1[u1][c][k] * T2[u2][c][k]
+// The reference permutes both operands to (unique, common, contracted) order (CLT:51-75), broadcasts them against
+// each other (CLT:81) and sums the trailing axes (CLT:82-84); this kernel does the same contraction without the
+// materialised outer product.  One thread per output element, c fastest (coalesced stores).
+__global__ void __launch_bounds__(256) k_contract(const double* __restrict__ T1, const double* __restrict__ T2,
+                                                  double* __restrict__ out, int64_t U1, int64_t U2, int64_t Cc,
+                                                  int64_t Kc) {
+  int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= U1 * U2 * Cc) return;
+  const int64_t c = idx % Cc;
+  const int64_t u2 = (idx / Cc) % U2;
+  const int64_t u1 = idx / (Cc * U2);
+  const double* a = T1 + (u1 * Cc + c) * Kc;
+  const double* b = T2 + (u2 * Cc + c) * Kc;
+  double s = 0.0;
+  for (int64_t k = 0; k < Kc; ++k) s = fma(a[k], b[k], s);
+  out[idx] = s;
+}
+
+}  // namespace tnml
+
+using namespace tnml;
+
+extern "C" int tnml_contract(const void* T1, const void* T2, void* out, int64_t U1, int64_t U2, int64_t Cc, int64_t Kc,
+                             int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(T1 && T2 && out && U1 > 0 && U2 > 0 && Cc > 0 && Kc > 0);
+  int64_t n = U1 * U2 * Cc;
+  k_contract<<<tnml_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const double*)T1, (const double*)T2, (double*)out, U1,
+                                                                 U2, Cc, Kc);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_version(void) { return 100; }
+
+extern "C" const char* tnml_error_string(int code) {
+  if (code == TNML_OK) return "ok";
+  if (code == TNML_ERR_INVALID) return "invalid argument (dimension, pointer or enum)";
+  if (code == TNML_ERR_UNSUPPORTED) return "dtype or size not supported by this build";
+  if (code == TNML_ERR_WORKSPACE) return "workspace too small";
+  if (code <= -1000) return cudaGetErrorString((cudaError_t)(-code - 1000));
+  return "unknown error";
+}

@@ -1,0 +1,243 @@
+// Feature map, input packing, environment advance (FP64 DMMA), forward's last contraction.
+#include "common.cuh"
+
+namespace tnml {
+
+// ---------------------------------------------------------------------------------------------------
+// phi[s][b][:] = [sin(pi x/2), cos(pi x/2)]   (DG:165-167).  32x32 transpose tile: reads coalesced along s,
+// writes coalesced along b.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_feature_map(const double* __restrict__ x, double2* __restrict__ phi, int64_t Ns,
+                                                    int S) {
+  __shared__ double tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int64_t b = b0 + r;
+    int s = s0 + tx;
+    tile[r][tx] = (b < Ns && s < S) ? x[b * S + s] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int s = s0 + r;
+    int64_t b = b0 + tx;
+    if (b < Ns && s < S) {
+      double v = tile[tx][r];
+      double arg = 3.141592653589793 * v / 2;  // same operation order as np.pi*x/2
+      phi[(int64_t)s * Ns + b] = make_double2(sin(arg), cos(arg));
+    }
+  }
+}
+
+// X[b][s][2] -> phi[s][b][2]   (NC:222-225 builds TX[i] = X[:, i, :])
+__global__ void __launch_bounds__(256) k_pack_features(const double2* __restrict__ X, double2* __restrict__ phi,
+                                                      int64_t Ns, int S) {
+  __shared__ double2 tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int64_t b = b0 + r;
+    int s = s0 + tx;
+    tile[r][tx] = (b < Ns && s < S) ? X[b * S + s] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int s = s0 + r;
+    int64_t b = b0 + tx;
+    if (b < Ns && s < S) phi[(int64_t)s * Ns + b] = tile[tx][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Environment advance: out[b][m] = sum_s phi[b][s] * sum_k E[b][k] W[k][s][m]
+// A batched (Ns x K) . (K x 2M) GEMM on DMMA with the sigma-combination fused into the epilogue.
+// CTA = 4 warps, 64 samples; warp = 16 samples x (2 sigma x 32 m).  K in chunks of 32, M in chunks of 32.
+// ---------------------------------------------------------------------------------------------------
+constexpr int EA_BM = 64, EA_KC = 32, EA_MC = 32;
+
+__global__ void __launch_bounds__(128) k_env_advance(const double* __restrict__ E, const double2* __restrict__ phi,
+                                                    const double* __restrict__ W, double* __restrict__ out, int64_t Ns,
+                                                    int K, int M) {
+  __shared__ double Es[EA_BM][EA_KC + 4];
+  __shared__ double Ws[EA_KC][2 * EA_MC + 4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t b0 = (int64_t)blockIdx.x * EA_BM;
+
+  for (int mc = 0; mc < M; mc += EA_MC) {
+    double acc[2][2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[i][s][n][0] = acc[i][s][n][1] = 0.0;
+
+    for (int kc = 0; kc < K; kc += EA_KC) {
+      __syncthreads();
+      // E tile: 64 rows x 32 k
+      {
+        const int k = tid & 31;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int r = (tid >> 5) + 4 * i;
+          int64_t b = b0 + r;
+          Es[r][k] = (b < Ns && kc + k < K) ? E[b * K + kc + k] : 0.0;
+        }
+      }
+      // W tile: 32 k x (2 sigma x 32 m)
+      {
+        const int mm = tid & 31;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int idx = (tid >> 5) + 4 * i;  // 0..63 -> (k, sigma)
+          int k = idx >> 1, s = idx & 1;
+          bool ok = (kc + k < K) && (mc + mm < M);
+          Ws[k][s * EA_MC + mm] = ok ? W[((int64_t)(kc + k) * 2 + s) * M + mc + mm] : 0.0;
+        }
+      }
+      __syncthreads();
+      const int kmax = min(EA_KC, K - kc);
+      for (int k4 = 0; k4 < kmax; k4 += 4) {
+        double a0 = Es[warp * 16 + g][k4 + t];
+        double a1 = Es[warp * 16 + 8 + g][k4 + t];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            double bv = Ws[k4 + t][s * EA_MC + n * 8 + g];
+            dmma(acc[0][s][n][0], acc[0][s][n][1], a0, bv);
+            dmma(acc[1][s][n][0], acc[1][s][n][1], a1, bv);
+          }
+      }
+    }
+    // epilogue: combine the two sigma planes with phi
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int64_t b = b0 + warp * 16 + i * 8 + g;
+      if (b < Ns) {
+        double2 p = phi[b];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          int m = mc + n * 8 + 2 * t;
+          if (m < M) out[b * M + m] = p.x * acc[i][0][n][0] + p.y * acc[i][1][n][0];
+          if (m + 1 < M) out[b * M + m + 1] = p.x * acc[i][0][n][1] + p.y * acc[i][1][n][1];
+        }
+      }
+    }
+  }
+}
+
+// Wt[c][s][a] = site[a][s][c]
+__global__ void k_site_transpose(const double* __restrict__ site, double* __restrict__ Wt, int Dl, int Dr) {
+  int n = Dl * 2 * Dr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int a = i % Dl, s = (i / Dl) & 1, c = i / (2 * Dl);
+    Wt[i] = site[((int64_t)a * 2 + s) * Dr + c];
+  }
+}
+
+// [a][s][l][c] <-> [a][l][s][c]
+__global__ void k_label_site_swap(const double* __restrict__ in, double* __restrict__ out, int Dl, int Dr, int L,
+                                  int to_left) {
+  int n = Dl * 2 * L * Dr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = i % Dr;
+    int r = i / Dr;
+    int a, s, l;
+    if (to_left) {  // out index (a, l, s, c)
+      s = r % 2; l = (r / 2) % L; a = r / (2 * L);
+      out[i] = in[(((int64_t)a * 2 + s) * L + l) * Dr + c];
+    } else {  // out index (a, s, l, c)
+      l = r % L; s = (r / L) % 2; a = r / (2 * L);
+      out[i] = in[(((int64_t)a * L + l) * 2 + s) * Dr + c];
+    }
+  }
+}
+
+// f[b][l] = sum L[b][a] phi[b][s] A[a][s][l][c] R[b][c]; one thread per (b, l).  Only used with Dl == 1 or
+// Dr == 1 by forward(), so it is a thin FMA kernel.
+__global__ void __launch_bounds__(256) k_site_predict(const double* __restrict__ Lenv, const double2* __restrict__ phi,
+                                                     const double* __restrict__ A, const double* __restrict__ Renv,
+                                                     double* __restrict__ f, int64_t Ns, int Dl, int Dr, int L) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ns * L) return;
+  int64_t b = idx / L;
+  int l = (int)(idx % L);
+  double2 p = phi[b];
+  double sum = 0.0;
+  for (int a = 0; a < Dl; ++a) {
+    double la = Lenv[b * Dl + a];
+    const double* A0 = A + (((int64_t)a * 2 + 0) * L + l) * Dr;
+    const double* A1 = A + (((int64_t)a * 2 + 1) * L + l) * Dr;
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = 0; c < Dr; ++c) {
+      double r = Renv[b * Dr + c];
+      s0 = fma(A0[c], r, s0);
+      s1 = fma(A1[c], r, s1);
+    }
+    sum = fma(la, p.x * s0 + p.y * s1, sum);
+  }
+  f[idx] = sum;
+}
+
+}  // namespace tnml
+
+using namespace tnml;
+
+extern "C" int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(x && phi && Ns > 0 && S > 0);
+  dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  k_feature_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (double2*)phi, Ns, S);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t S, int32_t dtype,
+                                  tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(X && phi && Ns > 0 && S > 0);
+  dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  k_pack_features<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2*)X, (double2*)phi, Ns, S);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_env_advance(const void* E, const void* phi_p, const void* W, void* out, int64_t Ns, int32_t K,
+                                int32_t M, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(E && phi_p && W && out && Ns > 0 && K > 0 && M > 0);
+  k_env_advance<<<tnml_cdiv(Ns, EA_BM), 128, 0, (cudaStream_t)stream>>>((const double*)E, (const double2*)phi_p,
+                                                                       (const double*)W, (double*)out, Ns, K, M);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_site_transpose(const void* site, void* Wt, int32_t Dl, int32_t Dr, int32_t dtype,
+                                   tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(site && Wt && Dl > 0 && Dr > 0);
+  int n = Dl * 2 * Dr;
+  k_site_transpose<<<min(tnml_cdiv(n, 256), 1024), 256, 0, (cudaStream_t)stream>>>((const double*)site, (double*)Wt, Dl,
+                                                                                   Dr);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32_t Dr, int32_t L, int32_t to_left_layout,
+                                    int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(in && out && in != out && Dl > 0 && Dr > 0 && L > 0);
+  int n = Dl * 2 * L * Dr;
+  k_label_site_swap<<<min(tnml_cdiv(n, 256), 1024), 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, Dl,
+                                                                                    Dr, L, to_left_layout);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_site_predict(const void* Lenv, const void* phi_p, const void* A_label, const void* Renv, void* f,
+                                 int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(Lenv && phi_p && A_label && Renv && f && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
+  k_site_predict<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const double*)Lenv, (const double2*)phi_p, (const double*)A_label, (const double*)Renv, (double*)f, Ns, Dl, Dr, L);
+  return tnml_launch_status();
+}

@@ -1,0 +1,373 @@
+"""Device-resident state and kernel sequencing for the MPS sweep (host side of the C ABI).
+
+PyTorch is used for plumbing only: device memory, streams, ``torch.distributed``.  Every arithmetic step of the
+hot path is a call into libtnml.so (``_lib.call``); there is no CPU or eager-PyTorch fallback.
+
+Index conventions:
+  bonds[p]  = dimension of the bond between sites p-1 and p   (bonds[0] = bonds[S] = 1)
+  env[p]    = (Ns, bonds[p]) per-sample environment living on that bond: the LEFT environment of sites < p while
+              the label is at or right of p, the RIGHT environment of sites >= p otherwise.  One arena holds both
+              families because at any time each bond needs only one of them.
+  nrmL[p] / nrmR[p] = (bonds[p], bonds[p]) norm environments of sites < p / >= p   (NC:966-1179)
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F64, ACT, LOSS, call
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class SweepEngine:
+    def __init__(self, S, L, T=0.1, act_fn="linear", loss_fn="cross_entropy", rule="reference", max_bond=None,
+                 device=None, group=None, svd_refine=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tensornetworkforml_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _lib.lib()
+        if rule not in ("reference", "fixed"):
+            raise ValueError("truncation rule must be 'reference' or 'fixed'")
+        if rule == "fixed" and not max_bond:
+            raise ValueError("rule='fixed' needs max_bond")
+        self.S, self.L, self.T = int(S), int(L), float(T)
+        self.act, self.loss = ACT[act_fn], LOSS[loss_fn]
+        self.rule, self.max_bond = rule, (int(max_bond) if max_bond else None)
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.group = group
+        self.world = 1
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+        self.svd_refine = 1 if svd_refine else 0
+        self.sites = [None] * self.S
+        self.bonds = [1] * (self.S + 1)
+        self.l_pos = 0
+        self.label_layout = "R"
+        self.Ns = 0
+        self.phi = None
+        self.env = None
+        self.env_cap = 0
+        self.y_dev = None
+        self.hist = None
+        self._pinned = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _empty(self, n):
+        return torch.empty(int(n), dtype=torch.float64, device=self.device)
+
+    def _workspace(self, key, nbytes):
+        n = max(1, (int(nbytes) + 7) // 8)
+        t = self._ws.get(key)
+        if t is None or t.numel() < n:
+            t = self._empty(n)
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ site tensors
+    def set_sites(self, host_sites, l_pos):
+        """host_sites: canonical arrays -- plain (Dl,2,Dr), label site (Dl,2,L,Dr)."""
+        assert len(host_sites) == self.S
+        self.l_pos = int(l_pos)
+        self.label_layout = "R"
+        for p, A in enumerate(host_sites):
+            A = np.ascontiguousarray(A, dtype=np.float64)
+            if p == self.l_pos:
+                assert A.ndim == 4 and A.shape[2] == self.L, "label site must be (Dl,2,L,Dr)"
+            else:
+                assert A.ndim == 3
+            self.bonds[p], self.bonds[p + 1] = A.shape[0], A.shape[-1]
+            self.sites[p] = torch.from_numpy(A.reshape(-1)).to(self.device)
+        assert self.bonds[0] == 1 and self.bonds[self.S] == 1
+
+    def get_sites(self):
+        self._label_to("R")
+        out = []
+        for p, t in enumerate(self.sites):
+            a = t.cpu().numpy()
+            Dl, Dr = self.bonds[p], self.bonds[p + 1]
+            out.append(a.reshape(Dl, 2, self.L, Dr) if p == self.l_pos else a.reshape(Dl, 2, Dr))
+        return out
+
+    def scale_sites(self, factor):
+        """As[i] /= factor for every site (the calibration rescale of NC:175-176)."""
+        for p in range(self.S):
+            self.sites[p] = self.sites[p] / factor
+
+    def _label_to(self, layout):
+        if layout == self.label_layout:
+            return
+        p = self.l_pos
+        src = self.sites[p]
+        dst = torch.empty_like(src)
+        call("tnml_label_site_swap", _ptr(src), _ptr(dst), self.bonds[p], self.bonds[p + 1], self.L,
+             1 if layout == "L" else 0, F64, self._stream())
+        self.sites[p] = dst
+        self.label_layout = layout
+
+    # ------------------------------------------------------------------ input
+    def _dcap(self):
+        mb = max(self.bonds)
+        cap = max(mb, min(2 * self.L, 2 * mb))
+        if self.max_bond:
+            cap = max(cap, self.max_bond)
+        return cap
+
+    def _alloc_batch(self, Ns):
+        cap = self._dcap()
+        if self.env is None or self.Ns != Ns or self.env_cap < cap:
+            self.env = None
+            self.env = torch.empty((self.S + 1, Ns * cap), dtype=torch.float64, device=self.device)
+            self.env_cap = cap
+            self.env[0, :Ns].fill_(1.0)
+            self.env[self.S, :Ns].fill_(1.0)
+            self.f_buf = [self._empty(Ns * self.L), self._empty(Ns * self.L)]
+            self.q_buf = self._empty(Ns * self.L * 4)
+            self.pp_buf = self._empty(Ns * 4)
+        if self.phi is None or self.phi.numel() != self.S * Ns * 2:
+            self.phi = self._empty(self.S * Ns * 2)
+        self.Ns = Ns
+
+    def load_input(self, X):
+        """X: (Ns, S, 2) feature-mapped input (what the reference API takes), NumPy on the host or a CUDA tensor."""
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            Xd = X.to(torch.float64).contiguous()
+            Ns = Xd.shape[0]
+        else:
+            X = np.asarray(X)
+            Ns = X.shape[0]
+            Xh = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
+            if self._pinned is None or self._pinned.numel() < Xh.numel():
+                self._pinned = torch.empty(Xh.numel(), dtype=torch.float64).pin_memory()
+            pin = self._pinned[:Xh.numel()]
+            pin.copy_(Xh.reshape(-1))
+            Xd = self._workspace("xstage", Xh.numel() * 8)[:Xh.numel()]
+            Xd.copy_(pin, non_blocking=True)
+        assert Xd.numel() == Ns * self.S * 2, "input must have shape (Ns, S, 2)"
+        self._alloc_batch(Ns)
+        call("tnml_pack_features", _ptr(Xd), _ptr(self.phi), Ns, self.S, F64, self._stream())
+        self.h2d_bytes = Ns * self.S * 2 * 8
+
+    def load_raw(self, x):
+        """x: (Ns, S) raw pixels; the feature map phi = [sin, cos](pi x / 2) runs on the device (DG:165-167)."""
+        xd = x if (isinstance(x, torch.Tensor) and x.is_cuda) else torch.from_numpy(
+            np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
+        Ns = xd.shape[0]
+        self._alloc_batch(Ns)
+        call("tnml_feature_map", _ptr(xd.contiguous()), _ptr(self.phi), Ns, self.S, F64, self._stream())
+
+    def _phi(self, p):
+        return self.phi.data_ptr() + p * self.Ns * 2 * 8
+
+    def _env(self, p):
+        return self.env.data_ptr() + p * self.env.shape[1] * 8
+
+    # ------------------------------------------------------------------ forward  (NC:195-258)
+    def _advance_right(self, p):
+        """env[p+1] = left env of sites <= p   (needs env[p], plain site p)."""
+        call("tnml_env_advance", self._env(p), self._phi(p), _ptr(self.sites[p]), self._env(p + 1), self.Ns,
+             self.bonds[p], self.bonds[p + 1], F64, self._stream())
+
+    def _advance_left(self, p):
+        """env[p] = right env of sites >= p   (needs env[p+1], plain site p)."""
+        Dl, Dr = self.bonds[p], self.bonds[p + 1]
+        wt = self._workspace("wt", Dl * 2 * Dr * 8)
+        call("tnml_site_transpose", _ptr(self.sites[p]), _ptr(wt), Dl, Dr, F64, self._stream())
+        call("tnml_env_advance", self._env(p + 1), self._phi(p), _ptr(wt), self._env(p), self.Ns, Dr, Dl, F64,
+             self._stream())
+
+    def forward(self):
+        S, l = self.S, self.l_pos
+        if l == 0:
+            for p in range(S - 1, 0, -1):
+                self._advance_left(p)
+        elif l == S - 1:
+            for p in range(0, S - 1):
+                self._advance_right(p)
+        else:
+            raise Exception("forward should not be called if l has an intermediate position (l_pos=%d)" % l)
+        self._label_to("R")
+        f = self.f_buf[0]
+        call("tnml_site_predict", self._env(l), self._phi(l), _ptr(self.sites[l]), self._env(l + 1), _ptr(f), self.Ns,
+             self.bonds[l], self.bonds[l + 1], self.L, F64, self._stream())
+        self.f_cur = 0
+        return f.view(self.Ns, self.L)
+
+    # ------------------------------------------------------------------ sweep  (NC:384-436)
+    def set_labels(self, y):
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            self.y_dev = y.to(torch.int32).contiguous()
+        else:
+            self.y_dev = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32)).to(self.device)
+        assert self.y_dev.numel() == self.Ns
+
+    def _choose_m(self, left_dir, Dl, R, C):
+        nS = min(R, C)
+        if self.rule == "fixed":
+            return min(nS, self.max_bond)
+        l, S = self.l_pos, self.S
+        if not left_dir:
+            if l == 0:
+                return nS                                    # NC:898-901
+            if l < S - 2:
+                if Dl > nS:
+                    raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
+                return Dl                                    # NC:902-906
+            if C != nS:                                      # NC:907-910: Vh stays (C,C), np.dot(Sqrt, Vh) fails
+                raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
+            return nS
+        if l == S - 1:
+            if C != nS:                                      # NC:933-936
+                raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
+            return nS
+        if l > 1:
+            if Dl > nS:
+                raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
+            return Dl                                        # NC:937-941
+        if R != nS:                                          # NC:942-945: U stays (R,R), np.dot(U, Sqrt) fails
+            raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (R, R, nS, nS))
+        return nS
+
+    def _build_norm_stack(self, left_dir):
+        S = self.S
+        one = torch.ones(1, dtype=torch.float64, device=self.device)
+        self.nrmL = [None] * (S + 1)
+        self.nrmR = [None] * (S + 1)
+        self.nrmL[0] = one
+        self.nrmR[S] = one
+        if not left_dir:
+            for p in range(S - 1, 1, -1):
+                self._norm_step(p, left_moving=True)
+        else:
+            for p in range(0, S - 2):
+                self._norm_step(p, left_moving=False)
+
+    def _norm_step(self, p, left_moving):
+        Dl, Dr = self.bonds[p], self.bonds[p + 1]
+        ws = self._workspace("nrm", 2 * Dl * Dr * 8)
+        if left_moving:
+            out = self._empty(Dl * Dl)
+            call("tnml_norm_env_step", _ptr(self.nrmR[p + 1]), _ptr(self.sites[p]), _ptr(out), _ptr(ws), Dl, Dr, 1, F64,
+                 self._stream())
+            self.nrmR[p] = out
+        else:
+            out = self._empty(Dr * Dr)
+            call("tnml_norm_env_step", _ptr(self.nrmL[p]), _ptr(self.sites[p]), _ptr(out), _ptr(ws), Dl, Dr, 0, F64,
+                 self._stream())
+            self.nrmL[p + 1] = out
+
+    def begin_sweep(self, y, left_dir, L2_flag, nsteps=None):
+        S = self.S
+        self.set_labels(y)
+        nsteps = S - 1 if nsteps is None else nsteps
+        self._label_to("L" if left_dir else "R")
+        if L2_flag:
+            self._build_norm_stack(left_dir)
+        nmax = 2 * max(self._dcap(), self.L) * 2
+        self.hist = dict(metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
+                         stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
+                         svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
+                         nsv=[], m=[], n=0)
+
+    def sweep_step(self, lr, weight_dec, L2_flag, left_dir):
+        """One bond update (NC:440-573 with update_B NC:577-763); everything stays on the device."""
+        S, L, Ns, st = self.S, self.L, self.Ns, self._stream()
+        l = self.l_pos
+        p = l - 1 if left_dir else l
+        q = p + 1
+        if (not left_dir and not (0 <= l <= S - 2)) or (left_dir and not (1 <= l <= S - 1)):
+            raise Exception("l = %d -> position not allowed for %s sweep step" % (l, "left" if left_dir else "right"))
+        step = self.hist["n"]
+        # environment (and norm environment) advance over the site fixed by the previous step  NC:637-642 / NC:669-674
+        if not left_dir and p > 0:
+            self._advance_right(p - 1)
+            if L2_flag:
+                self._norm_step(p - 1, left_moving=False)
+        if left_dir and q < S - 1:
+            self._advance_left(q + 1)
+            if L2_flag:
+                self._norm_step(q + 1, left_moving=True)
+        Dl, Dm, Dr = self.bonds[p], self.bonds[q], self.bonds[q + 1]
+        nB = Dl * 4 * L * Dr
+        # B = A_p . A_q                                                                      NC:484
+        B = self._empty(nB)
+        if not left_dir:
+            call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]), 2 * Dr,
+                 0.0, _ptr(B), 2 * Dr, F64, st)
+        else:
+            call("tnml_gemm", 0, 0, Dl * 2, L * 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
+                 L * 2 * Dr, 0.0, _ptr(B), L * 2 * Dr, F64, st)
+        # activation, loss derivative, metrics                                              NC:694-707
+        f_in = self.f_buf[self.f_cur]
+        gbuf = self._workspace("gbuf", (nB + 4) * 8)
+        dB, met = gbuf[:nB], gbuf[nB:nB + 4]
+        ws = self._workspace("al", _lib.lib().tnml_act_lossder_workspace_bytes(Ns))
+        call("tnml_act_lossder", _ptr(f_in), _ptr(self.y_dev), self._phi(p), self._phi(q), _ptr(self.q_buf),
+             _ptr(self.pp_buf), _ptr(met), _ptr(ws), Ns, L, self.act, self.loss, self.T, F64, st)
+        # gradient: K = Ns tensor-core reduction                                             NC:625-646, NC:710
+        ws = self._workspace("grad", _lib.lib().tnml_grad_workspace_bytes(Ns, Dl, Dr, L))
+        call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L, F64, st)
+        if self.world > 1:
+            met[2] = float(Ns)
+            torch.distributed.all_reduce(gbuf[:nB + 4], group=self.group)   # sum of dB, n_correct, sum|y-f|, Ns
+        else:
+            met[2] = float(Ns)
+        self.hist["metrics"][step].copy_(met)
+        # regularisation, clipping, update                                                   NC:728-761
+        Bn = self._empty(nB)
+        ws = self._workspace("bu", _lib.lib().tnml_bond_update_workspace_bytes(Dl, Dr, L))
+        EL = self.nrmL[p] if L2_flag else None
+        ER = self.nrmR[q + 1] if L2_flag else None
+        call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(EL), _ptr(ER), _ptr(Bn),
+             self.hist["stats"].data_ptr() + step * 6 * 8, _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec),
+             1 if L2_flag else 0, F64, st)
+        # new prediction from the UN-truncated B'                                            NC:494-523
+        f_out = self.f_buf[1 - self.f_cur]
+        ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
+        call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns, Dl,
+             Dr, L, F64, st)
+        self.f_cur = 1 - self.f_cur
+        # SVD split + truncation + label move                                                NC:528-563, NC:839-962
+        R, Cc = (2 * Dl, 2 * L * Dr) if not left_dir else (2 * Dl * L, 2 * Dr)
+        m = self._choose_m(left_dir, Dl, R, Cc)
+        new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
+        new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
+        ws = self._workspace("svd", _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
+        call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), self.hist["svals"].data_ptr() +
+             step * self.hist["svals"].shape[1] * 8, _ptr(ws), Dl, Dr, L, m, 1 if left_dir else 0, self.svd_refine, F64,
+             st)
+        self.sites[p], self.sites[q] = new_p, new_q
+        self.bonds[q] = m
+        self.l_pos += -1 if left_dir else 1                                                 # NC:568-571
+        self.hist["nsv"].append(min(R, Cc))
+        self.hist["m"].append(m)
+        self.hist["n"] = step + 1
+        return f_out.view(Ns, L)
+
+    def sweep(self, y, lr, weight_dec, L2_flag=True, left_dir=False):
+        self.begin_sweep(y, left_dir, L2_flag)
+        f = None
+        for _ in range(self.S - 1):
+            f = self.sweep_step(lr, weight_dec, L2_flag, left_dir)
+        return f
+
+    def history(self):
+        """Fetch the per-step record of the last sweep (one device->host copy)."""
+        n = self.hist["n"]
+        met = self.hist["metrics"][:n].cpu().numpy()
+        stats = self.hist["stats"][:n].cpu().numpy()
+        sv = self.hist["svals"][:n].cpu().numpy()
+        total = met[:, 2]
+        acc = met[:, 0] / total                                   # NC:700
+        mae = met[:, 1] / (total * self.L)                        # NC:702
+        svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
+        return dict(acc=acc, mae=mae, stats=stats, svals=svals, m=list(self.hist["m"]))
+
+    def bond_dims(self):
+        return list(self.bonds[1:self.S])

@@ -1,0 +1,137 @@
+"""CPU: the C-ABI library loads and exports every symbol include/tnml.h declares (no compute calls), and the
+host-side mirror of the reference's bookkeeping types behaves like the reference's."""
+import contextlib
+import io
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/TensorNetwork"
+
+
+def test_library_exports_every_declared_symbol():
+    from tensornetworkforml_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tnml.h")).read()
+    declared = set(re.findall(r"\b(tnml_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), "libtnml.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree: %s" % (declared ^ set(_lib.SIGNATURES))
+    assert handle.tnml_version() >= 100
+    assert handle.tnml_error_string(0) == b"ok"
+    # pure host-side queries are safe without a GPU
+    assert handle.tnml_grad_workspace_bytes(60000, 64, 64, 10) == 14 * 64 * 4 * 10 * 64 * 8
+    assert handle.tnml_svd_split_workspace_bytes(64, 64, 10, 0) > 128 * 1280 * 8
+
+
+def test_compute_paths_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import tensornetworkforml_b200 as tn
+    np.random.seed(0)
+    net = tn.Network(N=5, M=3, L=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net.forward(np.zeros((4, 5, 2)))
+    a = tn.Tensor(elem=np.ones((2, 3)), axes_names=["x", "k"])
+    b = tn.Tensor(elem=np.ones((3, 2)), axes_names=["k", "y"])
+    with pytest.raises(RuntimeError, match="GPU"):
+        tn.contract(a, b, contracted="k")
+
+
+def test_tensor_aggregate_disaggregate_transpose_add():
+    from tensornetworkforml_b200 import Tensor
+    rng = np.random.default_rng(0)
+    e = rng.standard_normal((2, 3, 4, 5))
+    T = Tensor(elem=e.copy(), axes_names=["d1", "left", "right", "l"])
+    T.aggregate(axes_names=["d1", "left"], new_ax_name="i")
+    T.aggregate(axes_names=["right", "l"], new_ax_name="j")
+    T.transpose(["i", "j"])
+    assert T.shape == (6, 20) and list(T.axes_names) == ["i", "j"]
+    assert np.array_equal(T.elem, e.reshape(6, 20))
+    assert T.aggregations["i"] == {"d1": 2, "left": 3}
+    T.disaggregate("j")
+    assert list(T.axes_names) == ["right", "l", "i"] and T.shape == (4, 5, 6)
+    T.disaggregate("i")
+    assert list(T.axes_names) == ["d1", "left", "right", "l"] and np.array_equal(T.elem, e)
+    A = Tensor(elem=e.copy(), axes_names=["a", "b", "c", "d"])
+    B = Tensor(elem=np.transpose(e, (3, 2, 1, 0)).copy(), axes_names=["d", "c", "b", "a"])
+    assert np.array_equal((A + B).elem, 2 * e) and np.array_equal((A - B).elem, 0 * e)
+    assert list(B.axes_names) == ["a", "b", "c", "d"]          # right operand permuted in place, like TC:282
+    with pytest.raises(AssertionError):
+        A + Tensor(elem=e, axes_names=["a", "b", "c", "z"])
+    with pytest.raises(Exception):
+        Tensor()
+    with pytest.raises(ValueError):
+        A.aggregate(axes_names=["a"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted")
+def test_tensor_and_data_generator_match_live_reference():
+    """Same seeds -> same weights, same data, same bookkeeping as the reference's own classes."""
+    import importlib.util
+    def load(name):
+        spec = importlib.util.spec_from_file_location("_ref_" + name, os.path.join(REF, name + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        saved = {k: sys.modules.get(k) for k in ("Tensor_class",)}
+        sys.path.insert(0, REF)
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            sys.path.remove(REF)
+        return mod
+    from tensornetworkforml_b200 import Tensor
+    import tensornetworkforml_b200.data_generator as gen
+    RT = load("Tensor_class")
+    np.random.seed(3)
+    a = RT.Tensor(shape=[4, 3, 2], axes_names=["left", "right", "d1"], scale=1.7)
+    np.random.seed(3)
+    b = Tensor(shape=[4, 3, 2], axes_names=["left", "right", "d1"], scale=1.7)
+    assert np.array_equal(a.elem, b.elem)
+    for T in (a, b):
+        T.aggregate(axes_names=["d1", "left"], new_ax_name="i")
+    assert np.array_equal(a.elem, b.elem) and list(a.axes_names) == list(b.axes_names)
+    assert {k: int(v) for k, v in a.aggregations["i"].items()} == {k: int(v) for k, v in b.aggregations["i"].items()}
+    for T in (a, b):
+        T.disaggregate("i")
+    assert np.array_equal(a.elem, b.elem) and list(a.axes_names) == list(b.axes_names)
+    RG = load("data_generator")
+    np.random.seed(0)
+    d0, l0 = RG.create_dataset(50, 6, 0.7)
+    np.random.seed(0)
+    d1, l1 = gen.create_dataset(50, 6, 0.7)
+    assert np.array_equal(d0, d1) and np.array_equal(l0, l1)
+    import torch
+    torch.manual_seed(0)
+    r = RG.prepare_dataset(d0, l0, 1, 0.2, 8, 4, 4)
+    torch.manual_seed(0)
+    m = gen.prepare_dataset(d1, l1, 1, 0.2, 8, 4, 4)
+    for lr_, lm in zip(r, m):
+        assert len(lr_) == len(lm)
+    torch.manual_seed(1)                     # the sampler draws its permutation when the iterator is created
+    br = next(iter(r[0]))
+    torch.manual_seed(1)
+    bm = next(iter(m[0]))
+    assert all(np.array_equal(x[0], z[0]) and x[1] == z[1] for x, z in zip(br, bm))
+
+
+def test_shipped_reference_pickle_loads_into_our_classes():
+    """module names Network_class / Tensor_class resolve to this package."""
+    path = os.path.join(REF, "trained_diag_model.dat")
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    import pickle
+    import tensornetworkforml_b200 as tn
+    for m in ("Network_class", "Tensor_class"):
+        mod = sys.modules.get(m)
+        if mod is not None and getattr(mod, "__file__", "").startswith(REF):
+            pytest.skip("reference modules already imported in this process")
+    with open(path, "rb") as fh:
+        net = pickle.load(fh)
+    assert isinstance(net, tn.Network) and net.N == 64 and net.L == 2 and net.l_pos == 63
+    assert len(net.As) == 64 and isinstance(net.As[0], tn.Tensor)

@@ -1,0 +1,196 @@
+"""GPU: the reference-facing API (Network.forward / sweep / train / pickle) against
+ (a) the fixtures the reference itself produced (tests/golden/*.npz) and
+ (b) the oracle on seeded inputs at sizes the oracle finishes in seconds.
+FP64 tolerance (BASELINE.json north_star): f, singular values (relative to S.max()) and metrics within 1e-10."""
+import io
+import contextlib
+import pickle
+
+import numpy as np
+import pytest
+
+from oracle import mps_oracle as O
+from tests import _golden as G
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def tn():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import tensornetworkforml_b200 as pkg
+    return pkg
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def network_from_sites(tn, sites, L, T, act, loss, l_pos=0, **opts):
+    """Build a Network holding given canonical site tensors (goes through the pickle-state path)."""
+    from tensornetworkforml_b200.Network_class import _canonical_to_named
+    S = len(sites)
+    net = tn.Network.__new__(tn.Network)
+    As = [_canonical_to_named(A, p, S, p == l_pos) for p, A in enumerate(sites)]
+    net.__setstate__(dict(N=S, D=2, L=L, M=max(A.shape[-1] for A in sites), T=T, As=As, l_pos=l_pos, act_fn=act,
+                          loss_fn=loss, TX=[], r_cum_contraction=None, l_cum_contraction=None,
+                          tnml_options=dict(truncation=opts.get("truncation", "reference"),
+                                            max_bond=opts.get("max_bond"), svd_refine=True)))
+    return net
+
+
+@pytest.mark.parametrize("name", G.SWEEP_CASES)
+def test_network_replays_reference_sweeps(tn, name):
+    case = G.load(name)
+    net = network_from_sites(tn, case["sites0"], case["L"], case["T"], case["act"], case["loss"],
+                             truncation=case["rule"], max_bond=case["max_bond"] if case["max_bond"] > 0 else None)
+    X, y = case["X"], case["y"]
+    for sw in range(case["nsweeps"]):
+        f = net.forward(X)
+        left = net.l_pos == net.N - 1
+        assert int(left) == case["left_%d" % sw]
+        vh = [[], []]
+        f2 = net.sweep(X, y, f, case["lr"], case["wd"], L2_flag=bool(case["L2"]), left_dir=left, var_hist=vh)
+        h = net.last_history
+        G.check_sweep_against_golden(case, sw, f.elem.T, f2.elem.T, vh[0], vh[1], h["svals"],
+                                     net._eng.bond_dims(), tol=TOL)
+    assert G.rel(net.forward(X).elem.T, case["f_final"]) < TOL
+
+
+def test_known_answer_trained_diag_model(tn):
+    z = np.load(G.GOLDEN_DIR + "/diag_model_known_answer.npz")
+    sites = [z["site_%d" % p] for p in range(64)]
+    net = network_from_sites(tn, sites, int(z["L"]), float(z["T"]), str(z["act"]), str(z["loss"]), l_pos=int(z["l_pos"]))
+    f = net.forward(z["X"])
+    assert list(f.axes_names) == ["l", "b"] and f.elem.shape == (2, 4)
+    assert G.rel(f.elem.T, z["f"]) < 1e-12
+
+
+@pytest.mark.parametrize("act,loss,L2,wd,rule,Lbl,D", [
+    ("softmax", "full_cross_ent", True, 1.0, "reference", 2, 6),
+    ("linear", "MSE", True, 0.01, "fixed", 10, 16),
+    ("softmax", "full_cross_ent", False, 1e-3, "fixed", 4, 8),
+    ("sigmoid", "MSE", True, 0.1, "fixed", 3, 12),
+])
+def test_seeded_constructor_and_sweeps_match_oracle(tn, act, loss, L2, wd, rule, Lbl, D):
+    """Public constructor with the reference's RNG order + calibration, then 3 free-running sweeps vs the oracle."""
+    S, Ns, lr = 12, 300, 0.02
+    np.random.seed(21)
+    X = O.feature_map(np.random.random((Ns, S)))
+    y = np.random.randint(0, Lbl, Ns)
+    state = np.random.get_state()
+    orc = O.OracleMPS.from_seed(S, D, Lbl, calibration_X=X, normalize=True, act_fn=act, loss_fn=loss, rule=rule,
+                                max_bond=D if rule == "fixed" else None)
+    np.random.set_state(state)
+    with quiet():
+        net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn=act, loss_fn=loss, truncation=rule,
+                         max_bond=D if rule == "fixed" else None)
+    assert abs(net.calibration_factor - orc.calibration_factor) < 1e-12 * orc.calibration_factor
+    for sw in range(3):
+        fo = orc.forward(X)
+        f = net.forward(X)
+        assert G.rel(f.elem.T, fo) < TOL
+        left = orc.l_pos == S - 1
+        n0 = len(orc.hist)
+        fo = orc.sweep(y, fo, lr, wd, L2_flag=L2, left_dir=left)
+        vh = [[], []]
+        f = net.sweep(X, y, f, lr, wd, L2_flag=L2, left_dir=left, var_hist=vh)
+        assert G.rel(f.elem.T, fo) < TOL
+        h = orc.hist[n0:]
+        assert np.abs(np.array(vh[0]) - [r["acc"] for r in h]).max() < 1e-12
+        assert np.abs(np.array(vh[1]) - [r["mae"] for r in h]).max() < TOL
+        for mine, ref in zip(net.last_history["svals"], [r["S"] for r in h]):
+            assert np.abs(mine[:len(ref)] - ref).max() / ref.max() < TOL
+        assert net._eng.bond_dims() == orc.bond_dims() and net.l_pos == orc.l_pos
+    # the sweep's running prediction equals a fresh forward where the last split is lossless (reference rule)
+    if rule == "reference":
+        assert G.rel(net.forward(X).elem, f.elem) < 1e-9
+
+
+def test_sweep_step_by_step_equals_sweep(tn):
+    """Network.sweep_step (the per-bond public method, one-hot y like NC:440) chained by hand == Network.sweep."""
+    S, Ns, Lbl, D = 8, 64, 2, 4
+    np.random.seed(3)
+    X = O.feature_map(np.random.random((Ns, S)))
+    y = np.random.randint(0, Lbl, Ns)
+    state = np.random.get_state()
+    with quiet():
+        a = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn="linear", loss_fn="MSE")
+    np.random.set_state(state)
+    with quiet():
+        b = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn="linear", loss_fn="MSE")
+    fa = a.sweep(X, y, a.forward(X), 0.01, 0.1)
+    fb = b.forward(X)
+    y1h = np.eye(Lbl)[y].T
+    vh = [[], []]
+    for _ in range(S - 1):
+        fb = b.sweep_step(fb, y1h, 0.01, Ns, 0.1, var_hist=vh)
+    assert np.array_equal(fa.elem, fb.elem) and len(vh[0]) == S - 1 and b.l_pos == S - 1
+
+
+def test_pickle_round_trip_and_reference_layout(tn):
+    S, Ns, Lbl, D = 8, 40, 2, 4
+    np.random.seed(5)
+    X = O.feature_map(np.random.random((Ns, S)))
+    y = np.random.randint(0, Lbl, Ns)
+    with quiet():
+        net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn="softmax", loss_fn="full_cross_ent")
+    net.sweep(X, y, net.forward(X), 0.01, 1.0)
+    blob = pickle.dumps(net, protocol=3)
+    import pickletools
+    names = {a for op, a, _ in pickletools.genops(blob) if op.name == "GLOBAL"}
+    assert "Network_class Network" in names and "Tensor_class Tensor" in names
+    net2 = pickle.loads(blob)
+    for key in ("N", "D", "L", "M", "T", "l_pos", "act_fn", "loss_fn"):
+        assert getattr(net2, key) == getattr(net, key)
+    assert net2.l_pos == S - 1
+    f1, f2 = net.forward(X), net2.forward(X)
+    assert np.array_equal(f1.elem, f2.elem)
+    # axis names follow the reference's vocabulary
+    for p, T in enumerate(net2.As):
+        assert set(map(str, T.axes_names)) <= {"left", "right", "l", "d%d" % p}
+
+
+def test_train_config1_shape(tn):
+    """training_diagonals.py re-enacted at reduced size: the loaders, train(), var_hist shape, learning happens."""
+    import tensornetworkforml_b200.data_generator as gen
+    np.random.seed(0)
+    torch.manual_seed(0)
+    data, label = gen.create_dataset(600, 6, 0.7)
+    tl, vl, _ = gen.prepare_dataset(data, label, 1, 0.2, train_batch_size=480, val_batch_size=40, test_batch_size=40)
+    cal = next(iter(tl))
+    xcal = np.array([c[0] for c in cal])
+    with quiet():
+        net = tn.Network(N=36, M=6, L=2, calibration_X=xcal, normalize=True, act_fn="softmax", loss_fn="full_cross_ent")
+        val_acc, var_hist = net.train(tl, vl, lr=0.01, n_epochs=3, weight_dec=1)
+    assert var_hist.shape == (3, 2, 35) and len(val_acc) == 3
+    assert net.l_pos == 35
+    assert val_acc[-1] > 0.9 and var_hist[-1, 1, -1] < var_hist[0, 1, 0]
+
+
+def test_errors_match_reference_conventions(tn):
+    with pytest.raises(AssertionError):
+        tn.Network(N=4, M=2, L=2, act_fn="relu")
+    with pytest.raises(AssertionError):
+        tn.Network(N=4, M=2, L=2, loss_fn="hinge")
+    np.random.seed(0)
+    net = tn.Network(N=5, M=3, L=2)
+    with pytest.raises(AssertionError):
+        net.forward(np.zeros((4, 6, 2)))
+    X = O.feature_map(np.random.random((8, 5)))
+    y = np.random.randint(0, 2, 8)
+    f = net.forward(X)
+    y1h = np.eye(2)[y].T
+    net.sweep_step(f, y1h, 0.01, 8, 0.0, L2_flag=False)
+    with pytest.raises(Exception):
+        net.forward(X)                      # l_pos is now in the middle of the chain (NC:258)
+    # L > 2 with the unmodified truncation rule cannot finish a right sweep
+    np.random.seed(1)
+    with quiet():
+        net3 = tn.Network(N=6, M=4, L=3, normalize=True, act_fn="linear", loss_fn="MSE")
+    X = O.feature_map(np.random.random((16, 6)))
+    with pytest.raises(ValueError, match="not aligned"):
+        net3.sweep(X, np.random.randint(0, 3, 16), net3.forward(X), 0.01, 0.0, L2_flag=False)
