@@ -43,6 +43,8 @@ enum {
 };
 
 int tnml_version(void);
+/* Kernels launched by this library in this process so far (statistics for bench.py's gpu_launches). */
+uint64_t tnml_kernel_launches(void);
 /* Human-readable text for a return code (static storage). */
 const char* tnml_error_string(int code);
 

@@ -389,7 +389,7 @@ class OracleMPS:
         A_left, A_right, Svals = svd_split(Bn, left_dir, m)                   # NC:563
         if not left_dir:
             self.sites[p] = A_left                                            # (a,s,m)
-            self.sites[q] = np.ascontiguousarray(np.transpose(A_right, (0, 1, 2, 3)))  # (m,t,l,c) label site
+            self.sites[q] = A_right                                           # (m,t,l,c) label site
             self.l_pos += 1                                                   # NC:568-569
         else:
             self.sites[p] = A_left                                            # (a,s,l,m) label site

@@ -18,6 +18,7 @@ LOSS = {"MSE": 0, "cross_entropy": 1, "full_cross_ent": 2}
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
     "tnml_version": (C.c_int, []),
+    "tnml_kernel_launches": (C.c_uint64, []),
     "tnml_error_string": (C.c_char_p, [C.c_int]),
     "tnml_feature_map": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "tnml_pack_features": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

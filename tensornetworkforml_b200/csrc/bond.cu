@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha,
 static int launch_gemm(int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
                        int ldb, double beta, double* C, int ldc, cudaStream_t st) {
   dim3 grid(tnml_cdiv(N, 64), tnml_cdiv(M, 64));
+  TNML_COUNT(1);
   if (!tA && !tB) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   else if (tA && !tB) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
   else if (!tA && tB) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
@@ -188,7 +189,9 @@ extern "C" int tnml_bond_update(const void* B, const void* dB, const void* EL, c
     if (rc) return rc;
   }
   const int nb = tnml_cdiv(n, BU_THREADS);
+  TNML_COUNT(1);
   k_bu_partial<<<nb, BU_THREADS, 0, st>>>((const double*)B, (const double*)dB, G, D, partial, n, wd, L2_flag);
+  TNML_COUNT(1);
   k_bu_apply<<<nb, BU_THREADS, 0, st>>>((const double*)B, D, partial, nb, (double*)Bnew, (double*)stats, n, lr, wd);
   return tnml_launch_status();
 }

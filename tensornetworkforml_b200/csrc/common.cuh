@@ -7,6 +7,11 @@
 
 #define TNML_CUDA_ERR(e) (-(1000 + (int)(e)))
 
+// Number of kernels this library has launched in this process (statistics only; read through
+// tnml_kernel_launches()).  Defined in contract.cu.
+extern unsigned long long g_tnml_kernel_launches;
+#define TNML_COUNT(n) (g_tnml_kernel_launches += (unsigned long long)(n))
+
 // Return the launch status of the kernel(s) just enqueued (no synchronisation).
 static inline int tnml_launch_status() {
   cudaError_t e = cudaGetLastError();

@@ -31,10 +31,14 @@ extern "C" int tnml_contract(const void* T1, const void* T2, void* out, int64_t 
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(T1 && T2 && out && U1 > 0 && U2 > 0 && Cc > 0 && Kc > 0);
   int64_t n = U1 * U2 * Cc;
+  TNML_COUNT(1);
   k_contract<<<tnml_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const double*)T1, (const double*)T2, (double*)out, U1,
                                                                  U2, Cc, Kc);
   return tnml_launch_status();
 }
+
+unsigned long long g_tnml_kernel_launches = 0;
+extern "C" uint64_t tnml_kernel_launches(void) { return g_tnml_kernel_launches; }
 
 extern "C" int tnml_version(void) { return 100; }
 

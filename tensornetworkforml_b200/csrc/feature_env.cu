@@ -191,6 +191,7 @@ extern "C" int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S,
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(x && phi && Ns > 0 && S > 0);
   dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  TNML_COUNT(1);
   k_feature_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (double2*)phi, Ns, S);
   return tnml_launch_status();
 }
@@ -200,6 +201,7 @@ extern "C" int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t 
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(X && phi && Ns > 0 && S > 0);
   dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  TNML_COUNT(1);
   k_pack_features<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2*)X, (double2*)phi, Ns, S);
   return tnml_launch_status();
 }
@@ -208,6 +210,7 @@ extern "C" int tnml_env_advance(const void* E, const void* phi_p, const void* W,
                                 int32_t M, int32_t dtype, tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(E && phi_p && W && out && Ns > 0 && K > 0 && M > 0);
+  TNML_COUNT(1);
   k_env_advance<<<tnml_cdiv(Ns, EA_BM), 128, 0, (cudaStream_t)stream>>>((const double*)E, (const double2*)phi_p,
                                                                        (const double*)W, (double*)out, Ns, K, M);
   return tnml_launch_status();
@@ -218,6 +221,7 @@ extern "C" int tnml_site_transpose(const void* site, void* Wt, int32_t Dl, int32
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(site && Wt && Dl > 0 && Dr > 0);
   int n = Dl * 2 * Dr;
+  TNML_COUNT(1);
   k_site_transpose<<<min(tnml_cdiv(n, 256), 1024), 256, 0, (cudaStream_t)stream>>>((const double*)site, (double*)Wt, Dl,
                                                                                    Dr);
   return tnml_launch_status();
@@ -228,6 +232,7 @@ extern "C" int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(in && out && in != out && Dl > 0 && Dr > 0 && L > 0);
   int n = Dl * 2 * L * Dr;
+  TNML_COUNT(1);
   k_label_site_swap<<<min(tnml_cdiv(n, 256), 1024), 256, 0, (cudaStream_t)stream>>>((const double*)in, (double*)out, Dl,
                                                                                     Dr, L, to_left_layout);
   return tnml_launch_status();
@@ -237,6 +242,7 @@ extern "C" int tnml_site_predict(const void* Lenv, const void* phi_p, const void
                                  int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(Lenv && phi_p && A_label && Renv && f && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
+  TNML_COUNT(1);
   k_site_predict<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>(
       (const double*)Lenv, (const double2*)phi_p, (const double*)A_label, (const double*)Renv, (double*)f, Ns, Dl, Dr, L);
   return tnml_launch_status();

@@ -235,9 +235,11 @@ extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi
   TNML_REQUIRE(f && y && phi_p && phi_q && q && pp && metrics && ws && Ns > 0 && L > 0 && L <= AL_MAXL);
   TNML_REQUIRE(act >= 0 && act <= 2 && loss >= 0 && loss <= 2);
   int nb = tnml_cdiv(Ns, AL_THREADS);
+  TNML_COUNT(1);
   k_act_lossder<<<nb, AL_THREADS, 0, (cudaStream_t)stream>>>((const double*)f, y, (const double2*)phi_p,
                                                             (const double2*)phi_q, (double*)q, (double*)pp, (double*)ws,
                                                             Ns, L, act, loss, T);
+  TNML_COUNT(1);
   k_metrics_final<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)ws, nb, (double*)metrics);
   return tnml_launch_status();
 }
@@ -263,10 +265,12 @@ extern "C" int tnml_grad(const void* q, const void* Lenv, const void* Renv, void
   int64_t chunk;
   grad_plan(Ns, Dl, Dr, L, &cols, &ks, &chunk);
   dim3 grid(cols, ks);
+  TNML_COUNT(1);
   k_grad<<<grid, 256, GR_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)q, (const double*)Lenv, (const double*)Renv,
                                                             (double*)ws, Ns, Dl, Dr, L, tnml_cdiv(Dl, 64),
                                                             tnml_cdiv(Dr, 64), chunk);
   int64_t n = (int64_t)Dl * 4 * L * Dr;
+  TNML_COUNT(1);
   k_grad_reduce<<<tnml_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const double*)ws, (double*)dB, n, ks);
   return tnml_launch_status();
 }

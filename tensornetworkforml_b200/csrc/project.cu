@@ -193,14 +193,17 @@ extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, con
   // the left bond is contracted 64 rows at a time; successive launches accumulate (deterministic: stream order)
   for (int ac = 0; ac < a_chunks; ++ac) {
     if (c_chunks == 1) {
+      TNML_COUNT(1);
       k_project<<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)B, (const double*)pp,
                                                                     (const double*)Lenv, (const double*)Renv, (double*)f,
                                                                     Ns, Dl, Dr, L, ac * 64, 1, chunk, 0, ac > 0);
     } else {
+      TNML_COUNT(1);
       k_project<<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)B, (const double*)pp,
                                                                     (const double*)Lenv, (const double*)Renv, (double*)ws,
                                                                     Ns, Dl, Dr, L, ac * 64, c_chunks, chunk,
                                                                     (int64_t)Ns * L, 0);
+      TNML_COUNT(1);
       k_fpart_reduce<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>((const double*)ws, (double*)f, Ns * L,
                                                                                 c_chunks, ac > 0);
     }

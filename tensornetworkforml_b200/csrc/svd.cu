@@ -71,94 +71,153 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long
   }
 }
 
-// One-sided Jacobi on the rows of the symmetric PSD matrix G (n x n) held in shared memory.
-// Output: Vt[k][:] = k-th eigenvector (unit), lam[k] = k-th eigenvalue, descending.
-__global__ void __launch_bounds__(1024, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
-                                                    double* __restrict__ Vt, double* __restrict__ lam, int max_sweeps) {
-  extern __shared__ __align__(16) double W[];  // n x n
-  __shared__ double nrm[SVD_MAXN];
-  __shared__ int rot_flag;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nwarps = blockDim.x >> 5;
+// One-sided (Hestenes) Jacobi on the rows of the symmetric PSD matrix G (n x n) held in shared memory, zero-padded
+// to the compile-time size NP (32, 64 or 128; a zero row never rotates).  One CTA of 8*NP threads; each HALF-warp
+// owns one row pair per round (NP/2 pairs per round), a lane holds NP/16 elements of each row as double2 vectors.
+// Per round and pair: one dot product (the squared row norms are cached, updated by the rotation and refreshed
+// once per sweep), a branch-free rotation-parameter evaluation (tan in single precision after a power-of-two
+// rescale, then c = rsqrt(1 + t^2), s = c t in double: the rotation is orthogonal to double precision whatever
+// the accuracy of t, which only affects the convergence rate), and the rotation itself.  The kernel is bound by
+// instruction issue, so everything is unrolled at compile time and the round-robin schedule is incremental.
+// Output: Vt[k][:] = k-th eigenvector (unit), lam[k] = k-th eigenvalue, descending; info[0] = sweeps used.
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-  for (int e = tid; e < n * n; e += blockDim.x) {
+// 1/sqrt(w) for w in [1, 2]: single-precision seed + two Newton steps in double (no special cases, no branches)
+__device__ __forceinline__ double rsqrt_1_2(double w) {
+  double r = (double)rsqrtf((float)w);
+  const double h = 0.5 * w;
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  r = fma(r, fma(-h * r, r, 0.5), r);
+  return r;
+}
+
+template <int NP>
+__global__ void __launch_bounds__(8 * NP, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
+                                                      double* __restrict__ Vt, double* __restrict__ lam, int max_sweeps,
+                                                      double tol, double* __restrict__ info) {
+  constexpr int V = NP / 32;  // double2 vectors per lane and row
+  extern __shared__ __align__(16) double W[];  // NP x NP
+  __shared__ double nrm2[NP];
+  __shared__ int rot_count;
+  const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NT = 8 * NP, NW = NT / 32;
+
+  for (int e = tid; e < NP * NP; e += NT) {
+    const int r = e / NP, c = e % NP;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n * n + e];
+    if (r < n && c < n)
+      for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n * n + r * n + c];
     W[e] = s;
   }
-  if (tid == 0) rot_flag = 0;
+  if (tid == 0) rot_count = 0;
   __syncthreads();
 
-  const int np = n + (n & 1);  // players in the round-robin tournament (one dummy if n is odd)
-  const int npairs = np >> 1;
-  const double tol = sqrt((double)n) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  int sweeps_done = 0;
+  // circle method: position 0 is fixed, positions 1..NP-1 rotate; half-warp hw plays position hw against NP-1-hw
+  int ra = (hw == 0) ? 0 : hw - 1, rb = NP - 2 - hw;   // (position - 1 + round) mod (NP - 1)
 
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    for (int round = 0; round < np - 1; ++round) {
-      for (int pi = warp; pi < npairs; pi += nwarps) {
-        // circle method: position 0 is fixed, positions 1..np-1 rotate
-        int pa = (pi == 0) ? 0 : 1 + (pi - 1 + round) % (np - 1);
-        int pb = 1 + (np - 2 - pi + round) % (np - 1);
-        int p = min(pa, pb), q = max(pa, pb);
-        if (q >= n) continue;  // dummy player
-        double* x = W + (size_t)p * n;
-        double* y = W + (size_t)q * n;
-        double xv[4], yv[4];
-        double al = 0.0, be = 0.0, ga = 0.0;
+    {  // refresh the cached squared norms of rows hw and hw + NP/2
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          int idx = lane + 32 * k;
-          xv[k] = idx < n ? x[idx] : 0.0;
-          yv[k] = idx < n ? y[idx] : 0.0;
-          al = fma(xv[k], xv[k], al);
-          be = fma(yv[k], yv[k], be);
-          ga = fma(xv[k], yv[k], ga);
-        }
-        al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-        if (fabs(ga) > tol * sqrt(al * be) && al > 0.0 && be > 0.0) {
-          double zeta = (be - al) / (2.0 * ga);
-          double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          double cs = 1.0 / sqrt(1.0 + tt * tt);
-          double sn = cs * tt;
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = hw + rr * (NP / 2);
+        const double2* row = reinterpret_cast<const double2*>(W + r * NP);
+        double s = 0.0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            int idx = lane + 32 * k;
-            if (idx < n) {
-              x[idx] = cs * xv[k] - sn * yv[k];
-              y[idx] = sn * xv[k] + cs * yv[k];
-            }
+        for (int k = 0; k < V; ++k) { double2 v = row[l16 + 16 * k]; s = fma(v.x, v.x, s); s = fma(v.y, v.y, s); }
+        s = half_sum(s);
+        if (l16 == 0) nrm2[r] = s;
+      }
+    }
+    __syncthreads();
+    for (int round = 0; round < NP - 1; ++round) {
+      const int p = (hw == 0) ? 0 : 1 + ra;
+      const int q = 1 + rb;
+      double2* x = reinterpret_cast<double2*>(W + p * NP);
+      double2* y = reinterpret_cast<double2*>(W + q * NP);
+      double2 xv[V], yv[V];
+      double ga = 0.0;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        xv[k] = x[l16 + 16 * k];
+        yv[k] = y[l16 + 16 * k];
+        ga = fma(xv[k].x, yv[k].x, ga);
+        ga = fma(xv[k].y, yv[k].y, ga);
+      }
+      ga = half_sum(ga);
+      const double al = nrm2[p], be = nrm2[q];
+      if (ga * ga > tol2 * al * be) {
+        const double de = be - al, ta = 2.0 * ga;
+        const double mx = fmax(fabs(de), fabs(ta));
+        const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
+        if (ex > 0 && ex < 2040) {
+          const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): mx*sc in [1,2)
+          const float df = (float)(de * sc), tf = (float)(ta * sc);
+          const float h = sqrtf(fmaf(df, df, tf * tf));
+          const double t = (double)__fdividef(tf, df + copysignf(h, df));  // |t| <= 1
+          const double cs = rsqrt_1_2(fma(t, t, 1.0));
+          const double sn = cs * t;
+#pragma unroll
+          for (int k = 0; k < V; ++k) {
+            double2 a = xv[k], b = yv[k], xo, yo;
+            xo.x = cs * a.x - sn * b.x; xo.y = cs * a.y - sn * b.y;
+            yo.x = sn * a.x + cs * b.x; yo.y = sn * a.y + cs * b.y;
+            x[l16 + 16 * k] = xo;
+            y[l16 + 16 * k] = yo;
           }
-          if (lane == 0) rot_flag = 1;
+          if (l16 == 0) {
+            nrm2[p] = al - t * ga;
+            nrm2[q] = be + t * ga;
+            rot_count = 1;
+          }
         }
       }
+      ra = (ra + 1 == NP - 1) ? 0 : ra + 1;
+      rb = (rb + 1 == NP - 1) ? 0 : rb + 1;
       __syncthreads();
     }
-    int any = rot_flag;
+    sweeps_done = sweep + 1;
+    const int any = rot_count;
     __syncthreads();
-    if (tid == 0) rot_flag = 0;
+    if (tid == 0) rot_count = 0;
     __syncthreads();
     if (!any) break;
   }
+  if (tid == 0 && info) info[0] = (double)sweeps_done;
 
   // row norms = eigenvalues; rank them (descending, ties by index) and emit the unit rows in that order
-  for (int r = warp; r < n; r += nwarps) {
+  for (int r = warp; r < n; r += NW) {
     double s = 0.0;
-    for (int idx = lane; idx < n; idx += 32) { double v = W[(size_t)r * n + idx]; s = fma(v, v, s); }
+    for (int idx = lane; idx < n; idx += 32) { double v = W[r * NP + idx]; s = fma(v, v, s); }
     s = warp_sum(s);
-    if (lane == 0) nrm[r] = sqrt(s);
+    if (lane == 0) nrm2[r] = sqrt(s);
   }
   __syncthreads();
-  for (int r = warp; r < n; r += nwarps) {
-    const double mine = nrm[r];
+  for (int r = warp; r < n; r += NW) {
+    const double mine = nrm2[r];
     int rank = 0;
     for (int o = 0; o < n; ++o) {
-      double other = nrm[o];
+      double other = nrm2[o];
       rank += (other > mine) || (other == mine && o < r);
     }
     const double inv = mine > 0.0 ? 1.0 / mine : 0.0;
-    for (int idx = lane; idx < n; idx += 32) Vt[(size_t)rank * n + idx] = W[(size_t)r * n + idx] * inv;
+    for (int idx = lane; idx < n; idx += 32) Vt[(size_t)rank * n + idx] = W[r * NP + idx] * inv;
     if (lane == 0) lam[rank] = mine;
   }
+}
+
+static void launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, double* info,
+                          cudaStream_t st) {
+  TNML_COUNT(1);
+  if (n > 64) k_jacobi<128><<<1, 1024, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
+  else if (n > 32) k_jacobi<64><<<1, 512, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
+  else k_jacobi<32><<<1, 256, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
 }
 
 // Out[k][l] = scale_k * sum_s Vt[k][s] In(s,l), k < kmax; scale_k = lam_k^(-1/4) if lam != nullptr else 1
@@ -257,7 +316,7 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_jacobi, cudaFuncAttributeMaxDynamicSharedMemorySize, SVD_MAXN * SVD_MAXN * 8);
+    cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     e = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * (SVD_MAXN + 1) + SVD_MAXN * 33) * 8);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
@@ -269,8 +328,7 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   const double* X = (const double*)Bnew;
   const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
   const int n = p.n, Nl = p.Nl;
-  const int jthreads = n >= 64 ? 1024 : (n >= 32 ? 512 : 256);
-  const size_t jsmem = (size_t)n * n * 8;
+  const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
   const size_t rsmem = (size_t)(32 * (n + 1) + n * 33) * 8;
 
   // destination maps (see tnml.h): rows of Mx -> site_p, columns of Mx -> site_q
@@ -288,20 +346,27 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   const Idx3 map_short = p.rows_short ? rowmap : colmap, map_long = p.rows_short ? colmap : rowmap;
   const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
 
+  TNML_COUNT(1);
   k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial);
-  k_jacobi<<<1, jthreads, jsmem, st>>>(partial, p.nparts, n, vt1, lam1, 40);
+  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, (double*)svals + n, st);
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
+    TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
+    TNML_COUNT(1);
     k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial);
-    k_jacobi<<<1, jthreads, jsmem, st>>>(partial, p.nparts, n, vt2, lam2, 40);
+    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, (double*)svals + n + 1, st);
+    TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
                                                                         k_long_stride, map_long);
+    TNML_COUNT(1);
     k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short,
                                                    (double*)svals);
   } else {
+    TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
                                                                         k_long_stride, map_long);
+    TNML_COUNT(1);
     k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short,
                                                    (double*)svals);
   }

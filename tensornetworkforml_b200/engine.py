@@ -23,6 +23,25 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+class _Timed:
+    """Optional CUDA-event bracket around one C-ABI call (bench.py's live per-kernel timing)."""
+
+    def __init__(self, eng, name, flops):
+        self.eng, self.name, self.flops = eng, name, flops
+
+    def __enter__(self):
+        if self.eng.timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.eng.device))
+
+    def __exit__(self, *exc):
+        if self.eng.timers is not None:
+            self.e1.record(torch.cuda.current_stream(self.eng.device))
+            self.eng.timers.setdefault(self.name, []).append((self.e0, self.e1, self.flops))
+        return False
+
+
 class SweepEngine:
     def __init__(self, S, L, T=0.1, act_fn="linear", loss_fn="cross_entropy", rule="reference", max_bond=None,
                  device=None, group=None, svd_refine=True):
@@ -54,10 +73,19 @@ class SweepEngine:
         self.hist = None
         self._pinned = None
         self._ws = {}
+        self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
+        self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
+        self._side = None
+        self._inflight = None
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def _empty(self, n):
         return torch.empty(int(n), dtype=torch.float64, device=self.device)
@@ -171,16 +199,18 @@ class SweepEngine:
     # ------------------------------------------------------------------ forward  (NC:195-258)
     def _advance_right(self, p):
         """env[p+1] = left env of sites <= p   (needs env[p], plain site p)."""
-        call("tnml_env_advance", self._env(p), self._phi(p), _ptr(self.sites[p]), self._env(p + 1), self.Ns,
-             self.bonds[p], self.bonds[p + 1], F64, self._stream())
+        with _Timed(self, "env_advance", 4.0 * self.Ns * self.bonds[p] * self.bonds[p + 1]):
+            call("tnml_env_advance", self._env(p), self._phi(p), _ptr(self.sites[p]), self._env(p + 1), self.Ns,
+                 self.bonds[p], self.bonds[p + 1], F64, self._stream())
 
     def _advance_left(self, p):
         """env[p] = right env of sites >= p   (needs env[p+1], plain site p)."""
         Dl, Dr = self.bonds[p], self.bonds[p + 1]
         wt = self._workspace("wt", Dl * 2 * Dr * 8)
         call("tnml_site_transpose", _ptr(self.sites[p]), _ptr(wt), Dl, Dr, F64, self._stream())
-        call("tnml_env_advance", self._env(p + 1), self._phi(p), _ptr(wt), self._env(p), self.Ns, Dr, Dl, F64,
-             self._stream())
+        with _Timed(self, "env_advance", 4.0 * self.Ns * Dl * Dr):
+            call("tnml_env_advance", self._env(p + 1), self._phi(p), _ptr(wt), self._env(p), self.Ns, Dr, Dl, F64,
+                 self._stream())
 
     def forward(self):
         S, l = self.S, self.l_pos
@@ -312,7 +342,9 @@ class SweepEngine:
              _ptr(self.pp_buf), _ptr(met), _ptr(ws), Ns, L, self.act, self.loss, self.T, F64, st)
         # gradient: K = Ns tensor-core reduction                                             NC:625-646, NC:710
         ws = self._workspace("grad", _lib.lib().tnml_grad_workspace_bytes(Ns, Dl, Dr, L))
-        call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L, F64, st)
+        with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
+            call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L, F64,
+                 st)
         if self.world > 1:
             met[2] = float(Ns)
             torch.distributed.all_reduce(gbuf[:nB + 4], group=self.group)   # sum of dB, n_correct, sum|y-f|, Ns
@@ -327,21 +359,31 @@ class SweepEngine:
         call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(EL), _ptr(ER), _ptr(Bn),
              self.hist["stats"].data_ptr() + step * 6 * 8, _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec),
              1 if L2_flag else 0, F64, st)
-        # new prediction from the UN-truncated B'                                            NC:494-523
-        f_out = self.f_buf[1 - self.f_cur]
-        ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
-        call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns, Dl,
-             Dr, L, F64, st)
-        self.f_cur = 1 - self.f_cur
-        # SVD split + truncation + label move                                                NC:528-563, NC:839-962
+        # SVD split + truncation + label move (NC:528-563, NC:839-962) runs on a side stream, concurrently with the
+        # new prediction from the UN-truncated B' (NC:494-523) on the main stream: neither depends on the other.
         R, Cc = (2 * Dl, 2 * L * Dr) if not left_dir else (2 * Dl * L, 2 * Dr)
         m = self._choose_m(left_dir, Dl, R, Cc)
         new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
         new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
-        ws = self._workspace("svd", _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
-        call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), self.hist["svals"].data_ptr() +
-             step * self.hist["svals"].shape[1] * 8, _ptr(ws), Dl, Dr, L, m, 1 if left_dir else 0, self.svd_refine, F64,
-             st)
+        ws_svd = self._workspace("svd", _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
+        f_out = self.f_buf[1 - self.f_cur]
+        ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream() if self.overlap_svd else main
+        if side is not main:
+            side.wait_stream(main)                      # B' is ready
+        with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
+            call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
+                 Dl, Dr, L, F64, st)
+        self.f_cur = 1 - self.f_cur
+        with torch.cuda.stream(side):
+            with _Timed(self, "svd_split", 0.0):
+                call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), self.hist["svals"].data_ptr() +
+                     step * self.hist["svals"].shape[1] * 8, _ptr(ws_svd), Dl, Dr, L, m, 1 if left_dir else 0,
+                     self.svd_refine, F64, side.cuda_stream)
+        if side is not main:
+            main.wait_stream(side)                      # the next step needs the new site tensors
+            self._inflight = (B, Bn, dB)                # keep alive until the main stream has passed the wait
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

@@ -76,29 +76,35 @@ def test_known_answer_trained_diag_model(tn):
     ("sigmoid", "MSE", True, 0.1, "fixed", 3, 12),
 ])
 def test_seeded_constructor_and_sweeps_match_oracle(tn, act, loss, L2, wd, rule, Lbl, D):
-    """Public constructor with the reference's RNG order + calibration, then 3 free-running sweeps vs the oracle."""
+    """Public constructor with the reference's RNG order + calibration, then sweeps vs the oracle: sweeps 1-2 run
+    free, later sweeps are re-synchronised to the oracle's state first (the iteration is
+    chaotic -- a 1e-15 perturbation grows to ~1e-11 after three reference sweeps)."""
     S, Ns, lr = 12, 300, 0.02
     np.random.seed(21)
     X = O.feature_map(np.random.random((Ns, S)))
     y = np.random.randint(0, Lbl, Ns)
     state = np.random.get_state()
+    mb = D if rule == "fixed" else None
     orc = O.OracleMPS.from_seed(S, D, Lbl, calibration_X=X, normalize=True, act_fn=act, loss_fn=loss, rule=rule,
-                                max_bond=D if rule == "fixed" else None)
+                                max_bond=mb)
     np.random.set_state(state)
     with quiet():
         net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn=act, loss_fn=loss, truncation=rule,
-                         max_bond=D if rule == "fixed" else None)
+                         max_bond=mb)
     assert abs(net.calibration_factor - orc.calibration_factor) < 1e-12 * orc.calibration_factor
-    for sw in range(3):
+    for sw in range(4):
+        if sw >= 2:      # teacher forcing: restart from the oracle's current tensors
+            net = network_from_sites(tn, orc.sites, Lbl, orc.T, act, loss, l_pos=orc.l_pos, truncation=rule,
+                                     max_bond=mb)
         fo = orc.forward(X)
         f = net.forward(X)
-        assert G.rel(f.elem.T, fo) < TOL
+        assert G.rel(f.elem.T, fo) < TOL, "forward, sweep %d" % sw
         left = orc.l_pos == S - 1
         n0 = len(orc.hist)
         fo = orc.sweep(y, fo, lr, wd, L2_flag=L2, left_dir=left)
         vh = [[], []]
         f = net.sweep(X, y, f, lr, wd, L2_flag=L2, left_dir=left, var_hist=vh)
-        assert G.rel(f.elem.T, fo) < TOL
+        assert G.rel(f.elem.T, fo) < TOL, "post-sweep f, sweep %d" % sw
         h = orc.hist[n0:]
         assert np.abs(np.array(vh[0]) - [r["acc"] for r in h]).max() < 1e-12
         assert np.abs(np.array(vh[1]) - [r["mae"] for r in h]).max() < TOL
