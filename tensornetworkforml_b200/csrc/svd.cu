@@ -10,6 +10,8 @@
 //             single Gram pass loses (it squares the condition number)
 //   rows      long factor  = S^-1/2 U^T Mx   = sqrt(S) Vh      written into the destination site layout
 //   short     short factor = U sqrt(S)                         written into the destination site layout
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tnml {
@@ -79,33 +81,96 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long
 // rescale, then c = rsqrt(1 + t^2), s = c t in double: the rotation is orthogonal to double precision whatever
 // the accuracy of t, which only affects the convergence rate), and the rotation itself.  The kernel is bound by
 // instruction issue, so everything is unrolled at compile time and the round-robin schedule is incremental.
+// Preconditioning (Drmac-Veselic): before the sweeps G is replaced in place by its diagonally pivoted Cholesky
+// factor, G = sum_k r_k r_k^T (row r_k stored in the physical row of its pivot, so no permutation is ever applied).
+// Orthogonalising the rows of R instead of the rows of G works on the spectrum sigma instead of sigma^2 and needs
+// about half the sweeps; the rows converge to sigma_k v_k^T with v_k the eigenvectors of G.
 // Output: Vt[k][:] = k-th eigenvector (unit), lam[k] = k-th eigenvalue, descending; info[0] = sweeps used.
-__device__ __forceinline__ double half_sum(double v) {
+// Sum four values over the 32 lanes of a warp and leave all four sums on every lane: packed butterfly, 10 double
+// shuffles instead of 20 (shuffles share the MIO queue with shared-memory traffic, which bounds this kernel).
+__device__ __forceinline__ void warp_sum4(double& g0, double& g1, double& g2, double& g3, int lane) {
+  const bool hi = lane & 16;
+  double ka = hi ? g2 : g0, kb = hi ? g3 : g1;
+  ka += __shfl_xor_sync(0xffffffffu, hi ? g0 : g2, 16);
+  kb += __shfl_xor_sync(0xffffffffu, hi ? g1 : g3, 16);
+  const bool h8 = lane & 8;
+  double v = h8 ? kb : ka;
+  v += __shfl_xor_sync(0xffffffffu, h8 ? ka : kb, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  g0 = __shfl_sync(0xffffffffu, v, 0);
+  g1 = __shfl_sync(0xffffffffu, v, 8);
+  g2 = __shfl_sync(0xffffffffu, v, 16);
+  g3 = __shfl_sync(0xffffffffu, v, 24);
+}
+
+// Four independent row-pair rotations held in registers: rows x[i], y[i] (E elements per lane), cached squared
+// norms nx[i], ny[i].  Returns true if any pair had a relative inner product above 1e-8 (a "large" rotation).
+template <int E>
+__device__ __forceinline__ bool rotate4(double (&x)[4][E], double (&y)[4][E], double (&nx)[4], double (&ny)[4],
+                                        double tol2, int lane) {
+  double g[4];
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int i = 0; i < 4; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) acc = fma(x[i][k], y[i][k], acc);
+    g[i] = acc;
+  }
+  warp_sum4(g[0], g[1], g[2], g[3], lane);
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double al = nx[i], be = ny[i], ga = g[i];
+    const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
+    const double g2 = ga * ga, ab = al * be;
+    if (g2 > tol2 * ab && ex > 0 && ex < 2040) {
+      const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
+      // tan, cos, sin in single precision: t = 2ga / (de + sign(de) sqrt(de^2 + 4ga^2)), |t| <= 1
+      const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
+      const float h = sqrtf(fmaf(df, df, tf * tf));
+      const float t0 = __fdividef(tf, df + copysignf(h, df));
+      const float cf = rsqrtf(fmaf(t0, t0, 1.0f));
+      double cs = (double)cf, sn = (double)(cf * t0);
+      // exact renormalisation in double: nu = (cs^2 + sn^2)^(-1/2) = 1 - e/2 + 3e^2/8, e ~ 1e-7 -> error ~ e^3
+      const double e = fma(cs, cs, fma(sn, sn, -1.0));
+      const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
+      cs *= nu;
+      sn *= nu;
+#pragma unroll
+      for (int k = 0; k < E; ++k) {
+        const double a = x[i][k], b = y[i][k];
+        x[i][k] = cs * a - sn * b;
+        y[i][k] = sn * a + cs * b;
+      }
+      const double tg = (double)t0 * ga;
+      nx[i] = al - tg;
+      ny[i] = be + tg;
+      any |= g2 > 1e-16 * ab;
+    }
+  }
+  return any;
 }
 
-// 1/sqrt(w) for w in [1, 2]: single-precision seed + two Newton steps in double (no special cases, no branches)
-__device__ __forceinline__ double rsqrt_1_2(double w) {
-  double r = (double)rsqrtf((float)w);
-  const double h = 0.5 * w;
-  r = fma(r, fma(-h * r, r, 0.5), r);
-  r = fma(r, fma(-h * r, r, 0.5), r);
-  return r;
-}
-
+// NP: padded matrix size (32, 64, 128).  Rows are grouped in NP/4 blocks of 4; one WARP owns one block pair per
+// block-round (circle method over the blocks), keeps the 8 rows in registers (lane holds elements lane + 32k) and
+// performs all 16 cross rotations (4 sets of 4 independent ones) -- plus, in the first block-round of a sweep, the
+// 6 + 6 rotations inside the two blocks -- before writing the rows back: the matrix crosses shared memory once per
+// block-round instead of once per rotation round.
 template <int NP>
-__global__ void __launch_bounds__(8 * NP, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
-                                                      double* __restrict__ Vt, double* __restrict__ lam, int max_sweeps,
-                                                      double tol, double* __restrict__ info) {
-  constexpr int V = NP / 32;  // double2 vectors per lane and row
+__global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
+                                                      double* __restrict__ Vt, double* __restrict__ lam,
+                                                      int max_sweeps, double tol, int use_chol,
+                                                      double* __restrict__ info) {
+  constexpr int NB = NP / 4;           // row blocks
+  constexpr int NW = NB / 2;           // warps = block pairs per block-round
+  constexpr int NT = NW * 32;
+  constexpr int E = NP / 32;           // elements per lane and row
   extern __shared__ __align__(16) double W[];  // NP x NP
   __shared__ double nrm2[NP];
   __shared__ int rot_count;
-  const int tid = threadIdx.x, hw = tid >> 4, l16 = tid & 15;
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int NT = 8 * NP, NW = NT / 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   for (int e = tid; e < NP * NP; e += NT) {
     const int r = e / NP, c = e % NP;
@@ -117,72 +182,163 @@ __global__ void __launch_bounds__(8 * NP, 1) k_jacobi(const double* __restrict__
   if (tid == 0) rot_count = 0;
   __syncthreads();
 
-  const double tol2 = tol * tol;
-  int sweeps_done = 0;
-  // circle method: position 0 is fixed, positions 1..NP-1 rotate; half-warp hw plays position hw against NP-1-hw
-  int ra = (hw == 0) ? 0 : hw - 1, rb = NP - 2 - hw;   // (position - 1 + round) mod (NP - 1)
-
-  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    {  // refresh the cached squared norms of rows hw and hw + NP/2
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = hw + rr * (NP / 2);
-        const double2* row = reinterpret_cast<const double2*>(W + r * NP);
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < V; ++k) { double2 v = row[l16 + 16 * k]; s = fma(v.x, v.x, s); s = fma(v.y, v.y, s); }
-        s = half_sum(s);
-        if (l16 == 0) nrm2[r] = s;
-      }
-    }
+  // ---- diagonally pivoted Cholesky, in place and LEFT-looking: W <- R with G = R^T R ----
+  // Step k picks the largest remaining diagonal entry c of the Schur complement (kept incrementally in diag[]),
+  // forms only that row of the Schur complement, S[c][j] = G[c][j] - sum_{m<k} R_m[c] R_m[j], scales it and stores
+  // it in physical row c (rows of not-yet-eliminated indices still hold G).  No trailing-matrix update, no
+  // permutation: the rows of R are simply scattered by pivot.
+  if (use_chol) {
+    constexpr int NG = NT / NP;                          // thread groups splitting the sum over previous rows (4)
+    __shared__ double part[NG][NP], diag[NP];
+    __shared__ unsigned char active[NP];
+    __shared__ int piv[NP];
+    __shared__ double piv_floor;
+    __shared__ int piv_idx;
+    for (int j = tid; j < NP; j += NT) { active[j] = j < n; diag[j] = j < n ? W[j * NP + j] : 0.0; }
     __syncthreads();
-    for (int round = 0; round < NP - 1; ++round) {
-      const int p = (hw == 0) ? 0 : 1 + ra;
-      const int q = 1 + rb;
-      double2* x = reinterpret_cast<double2*>(W + p * NP);
-      double2* y = reinterpret_cast<double2*>(W + q * NP);
-      double2 xv[V], yv[V];
-      double ga = 0.0;
+    auto select_pivot = [&](bool first) {                // warp 0
+      double best = -1.0;
+      int bi = -1;
+      for (int j = lane; j < n; j += 32)
+        if (active[j]) { double v = diag[j]; if (v > best) { best = v; bi = j; } }
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        xv[k] = x[l16 + 16 * k];
-        yv[k] = y[l16 + 16 * k];
-        ga = fma(xv[k].x, yv[k].x, ga);
-        ga = fma(xv[k].y, yv[k].y, ga);
+      for (int o = 16; o > 0; o >>= 1) {
+        double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
       }
-      ga = half_sum(ga);
-      const double al = nrm2[p], be = nrm2[q];
-      if (ga * ga > tol2 * al * be) {
-        const double de = be - al, ta = 2.0 * ga;
-        const double mx = fmax(fabs(de), fabs(ta));
-        const int ex = (__double2hiint(mx) >> 20) & 0x7ff;
-        if (ex > 0 && ex < 2040) {
-          const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): mx*sc in [1,2)
-          const float df = (float)(de * sc), tf = (float)(ta * sc);
-          const float h = sqrtf(fmaf(df, df, tf * tf));
-          const double t = (double)__fdividef(tf, df + copysignf(h, df));  // |t| <= 1
-          const double cs = rsqrt_1_2(fma(t, t, 1.0));
-          const double sn = cs * t;
+      if (lane == 0) {
+        if (first) piv_floor = best * (double)n * 2.220446049250313e-16;
+        piv_idx = (bi >= 0 && best > piv_floor) ? bi : -1;
+      }
+    };
+    if (warp == 0) select_pivot(true);
+    __syncthreads();
+    const int j = tid % NP, gq = tid / NP;
+    for (int k = 0; k < n; ++k) {
+      const int c = piv_idx;
+      if (c < 0) break;                                  // numerically rank deficient from here on
+      double acc = 0.0;                                  // this group's share of sum_m R_m[c] R_m[j]
+#pragma unroll 4
+      for (int m = gq; m < k; m += NG) {
+        const int rm = piv[m];
+        acc = fma(W[rm * NP + c], W[rm * NP + j], acc);
+      }
+      part[gq][j] = acc;
+      __syncthreads();
+      if (gq == 0) {
+        double scc = W[c * NP + c], sj = W[c * NP + j];
 #pragma unroll
-          for (int k = 0; k < V; ++k) {
-            double2 a = xv[k], b = yv[k], xo, yo;
-            xo.x = cs * a.x - sn * b.x; xo.y = cs * a.y - sn * b.y;
-            yo.x = sn * a.x + cs * b.x; yo.y = sn * a.y + cs * b.y;
-            x[l16 + 16 * k] = xo;
-            y[l16 + 16 * k] = yo;
-          }
-          if (l16 == 0) {
-            nrm2[p] = al - t * ga;
-            nrm2[q] = be + t * ga;
-            rot_count = 1;
-          }
-        }
+        for (int g = 0; g < NG; ++g) { scc -= part[g][c]; sj -= part[g][j]; }
+        const double d = sqrt(fmax(scc, piv_floor));
+        double r = 0.0;
+        if (j == c) r = d;
+        else if (active[j]) { r = sj / d; diag[j] = fma(-r, r, diag[j]); }
+        W[c * NP + j] = r;
+        if (j == c) { active[c] = 0; piv[k] = c; }
       }
-      ra = (ra + 1 == NP - 1) ? 0 : ra + 1;
-      rb = (rb + 1 == NP - 1) ? 0 : rb + 1;
+      __syncthreads();
+      if (warp == 0) select_pivot(false);
       __syncthreads();
     }
+    // Rows never eliminated (numerical rank deficiency): the Schur complement is below the resolution of this
+    // pass.  Give them a tiny multiple of the unit vectors so that the sweeps still complete an orthonormal basis
+    // (the second pass resolves the true small singular values inside that subspace).
+    const double tiny = sqrt(piv_floor);
+    for (int e = tid; e < NP * NP; e += NT)
+      if (active[e / NP]) W[e] = (e / NP == e % NP) ? tiny : 0.0;
+    __syncthreads();
+  }
+
+  const double tol2 = tol * tol;
+  int sweeps_done = 0;
+  // circle method over the NB blocks: position 0 is fixed, positions 1..NB-1 rotate; warp w plays w against NB-1-w
+  int ra = (warp == 0) ? 0 : warp - 1, rb = NB - 2 - warp;   // (position - 1 + round) mod (NB - 1)
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = warp; r < NP; r += NW) {   // refresh the cached squared row norms
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const double v = W[r * NP + lane + 32 * k]; s = fma(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) nrm2[r] = s;
+    }
+    __syncthreads();
+    bool rotated = false;
+    for (int round = 0; round < NB - 1; ++round) {
+      const int bi = (warp == 0) ? 0 : 1 + ra;
+      const int bj = 1 + rb;
+      double a[4][E], b[4][E], na[4], nb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          a[i][k] = W[(4 * bi + i) * NP + lane + 32 * k];
+          b[i][k] = W[(4 * bj + i) * NP + lane + 32 * k];
+        }
+        na[i] = nrm2[4 * bi + i];
+        nb[i] = nrm2[4 * bj + i];
+      }
+      if (round == 0) {
+        // pairs inside each block, once per sweep: (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2) for both blocks at once
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int p0 = 0, q0 = s + 1;                       // (0,1) (0,2) (0,3)
+          const int p1 = (s == 0) ? 2 : 1, q1 = (s == 2) ? 2 : 3;   // (2,3) (1,3) (1,2)
+          double x[4][E], y[4][E], nx[4], ny[4];
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            x[0][k] = a[p0][k]; y[0][k] = a[q0][k]; x[1][k] = a[p1][k]; y[1][k] = a[q1][k];
+            x[2][k] = b[p0][k]; y[2][k] = b[q0][k]; x[3][k] = b[p1][k]; y[3][k] = b[q1][k];
+          }
+          nx[0] = na[p0]; ny[0] = na[q0]; nx[1] = na[p1]; ny[1] = na[q1];
+          nx[2] = nb[p0]; ny[2] = nb[q0]; nx[3] = nb[p1]; ny[3] = nb[q1];
+          rotated |= rotate4<E>(x, y, nx, ny, tol2, lane);
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            a[p0][k] = x[0][k]; a[q0][k] = y[0][k]; a[p1][k] = x[1][k]; a[q1][k] = y[1][k];
+            b[p0][k] = x[2][k]; b[q0][k] = y[2][k]; b[p1][k] = x[3][k]; b[q1][k] = y[3][k];
+          }
+          na[p0] = nx[0]; na[q0] = ny[0]; na[p1] = nx[1]; na[q1] = ny[1];
+          nb[p0] = nx[2]; nb[q0] = ny[2]; nb[p1] = nx[3]; nb[q1] = ny[3];
+        }
+      }
+      // the 16 pairs across the two blocks: set s pairs a[i] with b[(i+s)&3]
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        double y[4][E], ny[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) y[i][k] = b[(i + s) & 3][k];
+          ny[i] = nb[(i + s) & 3];
+        }
+        rotated |= rotate4<E>(a, y, na, ny, tol2, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) b[(i + s) & 3][k] = y[i][k];
+          nb[(i + s) & 3] = ny[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          W[(4 * bi + i) * NP + lane + 32 * k] = a[i][k];
+          W[(4 * bj + i) * NP + lane + 32 * k] = b[i][k];
+        }
+        if (lane == 0) { nrm2[4 * bi + i] = na[i]; nrm2[4 * bj + i] = nb[i]; }
+      }
+      ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+      rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+      __syncthreads();
+    }
+    // Stop rule: cyclic Jacobi converges quadratically, so a sweep in which every rotated pair had a relative
+    // inner product below 1e-8 leaves all of them below 1e-15 -- no separate verification sweep is needed.
+    if (rotated && lane == 0) rot_count = 1;
     sweeps_done = sweep + 1;
+    __syncthreads();
     const int any = rot_count;
     __syncthreads();
     if (tid == 0) rot_count = 0;
@@ -191,12 +347,13 @@ __global__ void __launch_bounds__(8 * NP, 1) k_jacobi(const double* __restrict__
   }
   if (tid == 0 && info) info[0] = (double)sweeps_done;
 
-  // row norms = eigenvalues; rank them (descending, ties by index) and emit the unit rows in that order
+  // squared row norms rank the rows (descending, ties by index); emit the unit rows in that order.
+  // With the Cholesky factor the rows are sigma_k v_k^T (|row|^2 = lambda_k); without it lambda_k v_k^T.
   for (int r = warp; r < n; r += NW) {
     double s = 0.0;
     for (int idx = lane; idx < n; idx += 32) { double v = W[r * NP + idx]; s = fma(v, v, s); }
     s = warp_sum(s);
-    if (lane == 0) nrm2[r] = sqrt(s);
+    if (lane == 0) nrm2[r] = s;
   }
   __syncthreads();
   for (int r = warp; r < n; r += NW) {
@@ -206,18 +363,23 @@ __global__ void __launch_bounds__(8 * NP, 1) k_jacobi(const double* __restrict__
       double other = nrm2[o];
       rank += (other > mine) || (other == mine && o < r);
     }
-    const double inv = mine > 0.0 ? 1.0 / mine : 0.0;
+    const double nr = sqrt(mine);
+    const double inv = mine > 0.0 ? 1.0 / nr : 0.0;
     for (int idx = lane; idx < n; idx += 32) Vt[(size_t)rank * n + idx] = W[r * NP + idx] * inv;
-    if (lane == 0) lam[rank] = mine;
+    if (lane == 0) lam[rank] = use_chol ? mine : nr;
   }
 }
 
-static void launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, double* info,
-                          cudaStream_t st) {
+static cudaError_t jacobi_prepare() {
+  return cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+}
+
+static void launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
+                          double* info, cudaStream_t st) {
   TNML_COUNT(1);
-  if (n > 64) k_jacobi<128><<<1, 1024, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
-  else if (n > 32) k_jacobi<64><<<1, 512, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
-  else k_jacobi<32><<<1, 256, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, info);
+  if (n > 64) k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
+  else if (n > 32) k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
+  else k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
 }
 
 // Out[k][l] = scale_k * sum_s Vt[k][s] In(s,l), k < kmax; scale_k = lam_k^(-1/4) if lam != nullptr else 1
@@ -316,7 +478,7 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+    cudaError_t e = jacobi_prepare();
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     e = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * (SVD_MAXN + 1) + SVD_MAXN * 33) * 8);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
@@ -348,14 +510,14 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
 
   TNML_COUNT(1);
   k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial);
-  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, (double*)svals + n, st);
+  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, (double*)svals + n, st);
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
     TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
     TNML_COUNT(1);
     k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial);
-    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, (double*)svals + n + 1, st);
+    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, (double*)svals + n + 1, st);
     TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
                                                                         k_long_stride, map_long);
