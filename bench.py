@@ -182,7 +182,8 @@ def main():
     c = dict(CFG, Ns=args.ns)
     S, L, D, Ns = c["S"], c["L"], c["D"], c["Ns"]
     X_all, y_all = synthetic_data(Ns, S, L, c["seed"])
-    lo, hi = rank * Ns // world, (rank + 1) * Ns // world
+    from tensornetworkforml_b200.parallel import shard_bounds
+    lo, hi = shard_bounds(Ns, rank, world)
     X, y = np.ascontiguousarray(X_all[lo:hi]), np.ascontiguousarray(y_all[lo:hi])
     del X_all
     np.random.seed(c["seed"])                      # identical initial weights on every rank

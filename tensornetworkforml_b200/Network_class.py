@@ -104,10 +104,8 @@ class Network():
         m = float(np.abs(f.elem).max())
         eng = self._eng
         if eng is not None and eng.world > 1:
-            import torch
-            t = torch.tensor([m], dtype=torch.float64, device=eng.device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX, group=eng.group)
-            m = float(t.item())
+            from .parallel import global_abs_max
+            m = global_abs_max(m, eng.device, group=eng.group, world=eng.world)
         return m
 
     def _engine(self):

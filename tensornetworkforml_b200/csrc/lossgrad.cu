@@ -93,6 +93,9 @@ constexpr int GR_BK = 16, GR_STAGES = 3, GR_LS = 68, GR_RS = 68, GR_QS = 8;
 constexpr int GR_STAGE_DOUBLES = GR_BK * (GR_LS + GR_RS + GR_QS);
 constexpr int GR_SMEM_BYTES = GR_STAGES * GR_STAGE_DOUBLES * 8;
 
+// FULL: every a-slice and c-slice is a complete 64 (no per-fragment predicates in the MMA loop: a predicate around
+// mma.sync costs a WARPSYNC + NOP + ISETP/BRA per DMMA, which halves the tensor-pipe issue rate).
+template <bool FULL>
 __global__ void __launch_bounds__(256, 1) k_grad(const double* __restrict__ q, const double* __restrict__ Lenv,
                                                  const double* __restrict__ Renv, double* __restrict__ ws, int64_t Ns,
                                                  int Dl, int Dr, int L, int a_chunks, int c_chunks, int64_t chunk) {
@@ -169,11 +172,11 @@ __global__ void __launch_bounds__(256, 1) k_grad(const double* __restrict__ q, c
       const double qv = Qs[kr * GR_QS + wn];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (nt_ok[j]) {
+        if (FULL || nt_ok[j]) {
           const double bv = qv * Rs[kr * GR_RS + j * 8 + g];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (mt_ok[i]) dmma(acc[i][j][0], acc[i][j][1], af[i], bv);
+            if (FULL || mt_ok[i]) dmma(acc[i][j][0], acc[i][j][1], af[i], bv);
         }
       }
     }
@@ -257,7 +260,9 @@ extern "C" int tnml_grad(const void* q, const void* Lenv, const void* Renv, void
   TNML_REQUIRE(q && Lenv && Renv && dB && ws && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    e = cudaFuncSetAttribute(k_grad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     attr_set = true;
   }
@@ -266,9 +271,14 @@ extern "C" int tnml_grad(const void* q, const void* Lenv, const void* Renv, void
   grad_plan(Ns, Dl, Dr, L, &cols, &ks, &chunk);
   dim3 grid(cols, ks);
   TNML_COUNT(1);
-  k_grad<<<grid, 256, GR_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)q, (const double*)Lenv, (const double*)Renv,
-                                                            (double*)ws, Ns, Dl, Dr, L, tnml_cdiv(Dl, 64),
-                                                            tnml_cdiv(Dr, 64), chunk);
+  if (Dl % 64 == 0 && Dr % 64 == 0)
+    k_grad<true><<<grid, 256, GR_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)q, (const double*)Lenv,
+                                                                    (const double*)Renv, (double*)ws, Ns, Dl, Dr, L,
+                                                                    Dl / 64, Dr / 64, chunk);
+  else
+    k_grad<false><<<grid, 256, GR_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)q, (const double*)Lenv,
+                                                                     (const double*)Renv, (double*)ws, Ns, Dl, Dr, L,
+                                                                     tnml_cdiv(Dl, 64), tnml_cdiv(Dr, 64), chunk);
   int64_t n = (int64_t)Dl * 4 * L * Dr;
   TNML_COUNT(1);
   k_grad_reduce<<<tnml_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const double*)ws, (double*)dB, n, ks);

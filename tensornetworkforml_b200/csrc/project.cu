@@ -15,6 +15,8 @@ constexpr int PJ_B_DOUBLES = 64 * PJ_BS;
 constexpr int PJ_RED_DOUBLES = 8 * PJ_BM;
 constexpr int PJ_SMEM_BYTES = (PJ_B_DOUBLES + PJ_STAGES * PJ_STAGE_DOUBLES + PJ_RED_DOUBLES) * 8;
 
+// FULL: the a-slice and the c-slice are complete 64s (no predicates around mma.sync, see k_grad).
+template <bool FULL>
 __global__ void __launch_bounds__(256, 1) k_project(const double* __restrict__ Bn, const double* __restrict__ pp,
                                                     const double* __restrict__ Lenv, const double* __restrict__ Renv,
                                                     double* __restrict__ fout, int64_t Ns, int Dl, int Dr, int L,
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(256, 1) k_project(const double* __restrict__ B
   bool nt_ok[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) nt_ok[j] = (cw + j * 8) < cn;
-  const int k4max = (an + 3) & ~3;
+  const int k4max = FULL ? 64 : ((an + 3) & ~3);
 
   for (int it = 0; it < nst; ++it) {
     if (it + 1 < nst) issue(it + 1);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(256, 1) k_project(const double* __restrict__ B
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    if (nt_ok[0]) {
+    if (FULL || nt_ok[0]) {
 #pragma unroll 4
       for (int k4 = 0; k4 < k4max; k4 += 4) {
         double af[4], bf[4];
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256, 1) k_project(const double* __restrict__ B
         for (int j = 0; j < 4; ++j) bf[j] = Bs[(k4 + t) * PJ_BS + st * 64 + cw + j * 8 + g];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (nt_ok[j]) {
+          if (FULL || nt_ok[j]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
           }
@@ -181,7 +183,9 @@ extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, con
   TNML_REQUIRE(B && pp && Lenv && Renv && f && ws && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_project, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    e = cudaFuncSetAttribute(k_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     attr_set = true;
   }
@@ -191,18 +195,23 @@ extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, con
   const int c_chunks = tnml_cdiv(Dr, 64), a_chunks = tnml_cdiv(Dl, 64);
   dim3 grid(cols, ks);
   // the left bond is contracted 64 rows at a time; successive launches accumulate (deterministic: stream order)
+  const bool full = (Dl % 64 == 0) && (Dr % 64 == 0);
+  auto launch = [&](double* dst, int a0, int64_t stride, int accumulate) {
+    TNML_COUNT(1);
+    if (full)
+      k_project<true><<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>(
+          (const double*)B, (const double*)pp, (const double*)Lenv, (const double*)Renv, dst, Ns, Dl, Dr, L, a0,
+          c_chunks, chunk, stride, accumulate);
+    else
+      k_project<false><<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>(
+          (const double*)B, (const double*)pp, (const double*)Lenv, (const double*)Renv, dst, Ns, Dl, Dr, L, a0,
+          c_chunks, chunk, stride, accumulate);
+  };
   for (int ac = 0; ac < a_chunks; ++ac) {
     if (c_chunks == 1) {
-      TNML_COUNT(1);
-      k_project<<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)B, (const double*)pp,
-                                                                    (const double*)Lenv, (const double*)Renv, (double*)f,
-                                                                    Ns, Dl, Dr, L, ac * 64, 1, chunk, 0, ac > 0);
+      launch((double*)f, ac * 64, 0, ac > 0);
     } else {
-      TNML_COUNT(1);
-      k_project<<<grid, 256, PJ_SMEM_BYTES, (cudaStream_t)stream>>>((const double*)B, (const double*)pp,
-                                                                    (const double*)Lenv, (const double*)Renv, (double*)ws,
-                                                                    Ns, Dl, Dr, L, ac * 64, c_chunks, chunk,
-                                                                    (int64_t)Ns * L, 0);
+      launch((double*)ws, ac * 64, (int64_t)Ns * L, 0);
       TNML_COUNT(1);
       k_fpart_reduce<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>((const double*)ws, (double*)f, Ns * L,
                                                                                 c_chunks, ac > 0);

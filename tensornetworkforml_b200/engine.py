@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import F64, ACT, LOSS, call
+from .parallel import reduce_gradient_and_metrics
 
 
 def _ptr(t):
@@ -56,10 +57,12 @@ class SweepEngine:
         self.act, self.loss = ACT[act_fn], LOSS[loss_fn]
         self.rule, self.max_bond = rule, (int(max_bond) if max_bond else None)
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.group = group
+        # group: a torch.distributed process group, None (= the default group when torch.distributed is initialised)
+        # or False (= never communicate: this replica owns the whole batch)
+        self.group = None if group is False else group
         self.world = 1
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(group)
+        if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(self.group)
         self.svd_refine = 1 if svd_refine else 0
         self.sites = [None] * self.S
         self.bonds = [1] * (self.S + 1)
@@ -345,11 +348,7 @@ class SweepEngine:
         with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
             call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L, F64,
                  st)
-        if self.world > 1:
-            met[2] = float(Ns)
-            torch.distributed.all_reduce(gbuf[:nB + 4], group=self.group)   # sum of dB, n_correct, sum|y-f|, Ns
-        else:
-            met[2] = float(Ns)
+        reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world)   # one collective per update
         self.hist["metrics"][step].copy_(met)
         # regularisation, clipping, update                                                   NC:728-761
         Bn = self._empty(nB)
