@@ -100,15 +100,19 @@ int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Re
                  int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream);
 
 /* ---- a10/a14: regularisation, clipping, update --------------------------------------------------------
- * reg  = L2_flag ? 2 wd * (E_L . B . E_R) : wd * B                     NC:728-734, NC:1129-1177
- * dB  -= reg ; if sum|dB| > sum|B| : dB /= (sum|dB| / sum|B|) ; B' = B + lr * dB        NC:755-761
- * stats[0..5] = { sum|B|, sum|dB| (after reg, before clip), wd*<B, E_L B E_R> (0 if !L2_flag), clipped?,
+ * tnml_l2_term     : G = E_L . B . E_R (the derivative of the squared norm w.r.t. B)        NC:1129-1135
+ *                    EL [Dl][Dl], ER [Dr][Dr] norm environments; ws: Dl*4*L*Dr elements.  Independent of the
+ *                    gradient, so the caller may run it on another stream while tnml_grad runs.
+ * tnml_bond_update : reg = L2_flag ? 2 wd G : wd B                                       NC:728-734, NC:1176
+ *                    dB -= reg ; if sum|dB| > sum|B| : dB /= (sum|dB| / sum|B|) ; B' = B + lr dB     NC:755-761
+ * stats[0..5] = { sum|B|, sum|dB| (after reg, before clip), wd*<B, G> (0 if !L2_flag), clipped?,
  *                 mean|B|, mean|dB| }                                     (NC:741-747 debug history)
- * EL [Dl][Dl], ER [Dr][Dr] norm environments (ignored when !L2_flag).  Bnew may alias neither B nor dB. */
+ * G is ignored when !L2_flag.  Bnew may alias neither B nor dB.  All sums are fixed-order (deterministic). */
+int tnml_l2_term(const void* B, const void* EL, const void* ER, void* G, void* ws, int32_t Dl, int32_t Dr, int32_t L,
+                 int32_t dtype, tnml_stream_t stream);
 int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L);
-int tnml_bond_update(const void* B, const void* dB, const void* EL, const void* ER, void* Bnew, void* stats, void* ws,
-                     int32_t Dl, int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag, int32_t dtype,
-                     tnml_stream_t stream);
+int tnml_bond_update(const void* B, const void* dB, const void* G, void* Bnew, void* stats, void* ws, int32_t Dl,
+                     int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag, int32_t dtype, tnml_stream_t stream);
 
 /* ---- a14: norm environments ----------------------------------------------------------------------------
  * right-moving: Eout[m][m'] = sum_{a,a',s} Ein[a][a'] A[a][s][m] A[a'][s][m']          NC:1004-1029
@@ -125,7 +129,10 @@ int tnml_norm_env_step(const void* Ein, const void* site, void* Eout, void* ws, 
  * written straight into the destination site layouts:
  *   right sweep: site_p[a][s][m] (plain),      site_q[m][tau][l][c] (label site, right-sweep layout)
  *   left  sweep: site_p[a][l][s][m] (label site, left-sweep layout), site_q[m][tau][c] (plain)
- * svals receives all min(R, C) singular values, descending.  m is chosen by the caller (truncation rule). */
+ * svals must hold min(R, C) + 2 values: all singular values, descending, then two diagnostics (Jacobi sweeps used by
+ * the first and second pass).  m is chosen by the caller (truncation rule).
+ * refine: 0 = single Gram pass (small singular values only accurate to sqrt(eps) sigma_max); 1 = second pass unless the
+ * first pass finds sigma_min/sigma_max > 3e-4 (then it is provably unnecessary at the 1e-11 level); 2 = always. */
 int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
 int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
                    int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream);

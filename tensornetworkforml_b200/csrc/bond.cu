@@ -162,36 +162,39 @@ extern "C" int tnml_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, i
                      (cudaStream_t)stream);
 }
 
-extern "C" int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L) {
-  int64_t n = (int64_t)Dl * 4 * L * Dr;
-  return (3 * n + 3 * (int64_t)tnml_cdiv(n, BU_THREADS)) * 8;
+extern "C" int tnml_l2_term(const void* B, const void* EL, const void* ER, void* G, void* ws, int32_t Dl, int32_t Dr,
+                            int32_t L, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(B && EL && ER && G && ws && Dl > 0 && Dr > 0 && L > 0 && G != B);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* T1 = (double*)ws;
+  // T1[a'][(s,l,t,c)] = sum_a EL[a'][a] B[a][...] ; G[(a,s,l,t)][c'] = sum_c T1[...][c] ER[c][c']      NC:1129-1135
+  int rc = launch_gemm(0, 0, Dl, 4 * L * Dr, Dl, 1.0, (const double*)EL, Dl, (const double*)B, 4 * L * Dr, 0.0, T1,
+                       4 * L * Dr, st);
+  if (rc) return rc;
+  return launch_gemm(0, 0, Dl * 4 * L, Dr, Dr, 1.0, T1, Dr, (const double*)ER, Dr, 0.0, (double*)G, Dr, st);
 }
 
-extern "C" int tnml_bond_update(const void* B, const void* dB, const void* EL, const void* ER, void* Bnew, void* stats,
-                                void* ws, int32_t Dl, int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag,
-                                int32_t dtype, tnml_stream_t stream) {
+extern "C" int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L) {
+  int64_t n = (int64_t)Dl * 4 * L * Dr;
+  return (n + 3 * (int64_t)tnml_cdiv(n, BU_THREADS)) * 8;
+}
+
+extern "C" int tnml_bond_update(const void* B, const void* dB, const void* G, void* Bnew, void* stats, void* ws,
+                                int32_t Dl, int32_t Dr, int32_t L, double lr, double wd, int32_t L2_flag, int32_t dtype,
+                                tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(B && dB && Bnew && stats && ws && Dl > 0 && Dr > 0 && L > 0);
   TNML_REQUIRE(Bnew != B && Bnew != dB);
-  if (L2_flag) TNML_REQUIRE(EL && ER);
+  if (L2_flag) TNML_REQUIRE(G != nullptr);
   cudaStream_t st = (cudaStream_t)stream;
   const int n = Dl * 4 * L * Dr;
-  double* T1 = (double*)ws;
-  double* G = T1 + n;
-  double* D = G + n;
+  double* D = (double*)ws;
   double* partial = D + n;
-  if (L2_flag) {
-    // T1[a'][(s,l,t,c)] = sum_a EL[a'][a] B[a][...] ; G[(a,s,l,t)][c'] = sum_c T1[...][c] ER[c][c']     NC:1129-1135
-    int rc = launch_gemm(0, 0, Dl, 4 * L * Dr, Dl, 1.0, (const double*)EL, Dl, (const double*)B, 4 * L * Dr, 0.0, T1,
-                         4 * L * Dr, st);
-    if (rc) return rc;
-    rc = launch_gemm(0, 0, Dl * 4 * L, Dr, Dr, 1.0, T1, Dr, (const double*)ER, Dr, 0.0, G, Dr, st);
-    if (rc) return rc;
-  }
   const int nb = tnml_cdiv(n, BU_THREADS);
-  TNML_COUNT(1);
-  k_bu_partial<<<nb, BU_THREADS, 0, st>>>((const double*)B, (const double*)dB, G, D, partial, n, wd, L2_flag);
-  TNML_COUNT(1);
+  TNML_COUNT(2);
+  k_bu_partial<<<nb, BU_THREADS, 0, st>>>((const double*)B, (const double*)dB, (const double*)G, D, partial, n, wd,
+                                          L2_flag);
   k_bu_apply<<<nb, BU_THREADS, 0, st>>>((const double*)B, D, partial, nb, (double*)Bnew, (double*)stats, n, lr, wd);
   return tnml_launch_status();
 }

@@ -29,8 +29,9 @@ constexpr int GRAM_LC = 32;  // long-side columns per CTA
 
 // partial[blk][i*n + j] = sum_{l in chunk} In(i,l) In(j,l),  In(s,l) = X[s*ss + l*sl]
 __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long long ss, long long sl, int n, int Nl,
-                                              double* __restrict__ partial) {
+                                              double* __restrict__ partial, const double* __restrict__ skip_flag) {
   __shared__ double V[16][SVD_MAXN + 1];
+  if (skip_flag && *skip_flag != 0.0) return;   // second pass not needed (see k_jacobi)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int l0 = blockIdx.x * GRAM_LC;
   const int lend = min(Nl, l0 + GRAM_LC);
@@ -86,6 +87,12 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long
 // Orthogonalising the rows of R instead of the rows of G works on the spectrum sigma instead of sigma^2 and needs
 // about half the sweeps; the rows converge to sigma_k v_k^T with v_k the eigenvectors of G.
 // Output: Vt[k][:] = k-th eigenvector (unit), lam[k] = k-th eigenvalue, descending; info[0] = sweeps used.
+__device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no slow path
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Sum four values over the 32 lanes of a warp and leave all four sums on every lane: packed butterfly, 10 double
 // shuffles instead of 20 (shuffles share the MIO queue with shared-memory traffic, which bounds this kernel).
 __device__ __forceinline__ void warp_sum4(double& g0, double& g1, double& g2, double& g3, int lane) {
@@ -129,9 +136,10 @@ __device__ __forceinline__ bool rotate4(double (&x)[4][E], double (&y)[4][E], do
       const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
       // tan, cos, sin in single precision: t = 2ga / (de + sign(de) sqrt(de^2 + 4ga^2)), |t| <= 1
       const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
-      const float h = sqrtf(fmaf(df, df, tf * tf));
+      const float hh = fmaf(df, df, tf * tf);                      // in [~1e-30, 8]: no range issues
+      const float h = hh * rsqrt_approx(hh);                       // sqrt via MUFU.RSQ
       const float t0 = __fdividef(tf, df + copysignf(h, df));
-      const float cf = rsqrtf(fmaf(t0, t0, 1.0f));
+      const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
       double cs = (double)cf, sn = (double)(cf * t0);
       // exact renormalisation in double: nu = (cs^2 + sn^2)^(-1/2) = 1 - e/2 + 3e^2/8, e ~ 1e-7 -> error ~ e^3
       const double e = fma(cs, cs, fma(sn, sn, -1.0));
@@ -162,7 +170,17 @@ template <int NP>
 __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
                                                       double* __restrict__ Vt, double* __restrict__ lam,
                                                       int max_sweeps, double tol, int use_chol,
-                                                      double* __restrict__ info) {
+                                                      double* __restrict__ info, double* __restrict__ skip_flag,
+                                                      const double* __restrict__ lam_prev) {
+  // Second-pass protocol: the first pass (use_chol = 1) sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7
+  // (sigma ratio > 3e-4: a single Gram pass is then already accurate to ~1e-12 sigma_max for every singular value);
+  // the second pass (use_chol = 0) sees the flag, returns the identity rotation and the first-pass eigenvalues.
+  if (!use_chol && skip_flag && *skip_flag != 0.0) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) lam[e] = lam_prev[e];
+    if (threadIdx.x == 0 && info) info[0] = 0.0;
+    return;
+  }
   constexpr int NB = NP / 4;           // row blocks
   constexpr int NW = NB / 2;           // warps = block pairs per block-round
   constexpr int NT = NW * 32;
@@ -269,12 +287,14 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
       const int bi = (warp == 0) ? 0 : 1 + ra;
       const int bj = 1 + rb;
       double a[4][E], b[4][E], na[4], nb[4];
+      double* const wa = W + 4 * bi * NP + lane;
+      double* const wb = W + 4 * bj * NP + lane;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-          a[i][k] = W[(4 * bi + i) * NP + lane + 32 * k];
-          b[i][k] = W[(4 * bj + i) * NP + lane + 32 * k];
+          a[i][k] = wa[i * NP + 32 * k];
+          b[i][k] = wb[i * NP + 32 * k];
         }
         na[i] = nrm2[4 * bi + i];
         nb[i] = nrm2[4 * bj + i];
@@ -325,8 +345,8 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
       for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int k = 0; k < E; ++k) {
-          W[(4 * bi + i) * NP + lane + 32 * k] = a[i][k];
-          W[(4 * bj + i) * NP + lane + 32 * k] = b[i][k];
+          wa[i * NP + 32 * k] = a[i][k];
+          wb[i * NP + 32 * k] = b[i][k];
         }
         if (lane == 0) { nrm2[4 * bi + i] = na[i]; nrm2[4 * bj + i] = nb[i]; }
       }
@@ -368,6 +388,16 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     for (int idx = lane; idx < n; idx += 32) Vt[(size_t)rank * n + idx] = W[r * NP + idx] * inv;
     if (lane == 0) lam[rank] = use_chol ? mine : nr;
   }
+  if (use_chol && skip_flag && warp == 0) {
+    double mn = 1e300, mx = 0.0;
+    for (int r = lane; r < n; r += 32) { mn = fmin(mn, nrm2[r]); mx = fmax(mx, nrm2[r]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) *skip_flag = (mn > 1e-7 * mx) ? 1.0 : 0.0;
+  }
 }
 
 static cudaError_t jacobi_prepare() {
@@ -375,11 +405,14 @@ static cudaError_t jacobi_prepare() {
 }
 
 static void launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
-                          double* info, cudaStream_t st) {
+                          double* info, double* skip, const double* lam_prev, cudaStream_t st) {
   TNML_COUNT(1);
-  if (n > 64) k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
-  else if (n > 32) k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
-  else k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info);
+  if (n > 64)
+    k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
+  else if (n > 32)
+    k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
+  else
+    k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
 }
 
 // Out[k][l] = scale_k * sum_s Vt[k][s] In(s,l), k < kmax; scale_k = lam_k^(-1/4) if lam != nullptr else 1
@@ -437,7 +470,7 @@ __global__ void __launch_bounds__(256) k_short(const double* __restrict__ Vt1, c
 struct SvdPlan {
   int R, C, n, Nl, nparts;
   bool rows_short;
-  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, total;
+  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, total;
 };
 
 static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
@@ -455,6 +488,7 @@ static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
   p.off_lam1 = o; o += p.n;
   p.off_lam2 = o; o += p.n;
   p.off_Y = o; o += (size_t)p.n * p.Nl;
+  p.off_skip = o; o += 1;
   p.total = o;
   return p;
 }
@@ -486,7 +520,7 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   }
   double* w = (double*)ws;
   double *partial = w + p.off_partial, *vt1 = w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
-         *lam2 = w + p.off_lam2, *Y = w + p.off_Y;
+         *lam2 = w + p.off_lam2, *Y = w + p.off_Y, *skip = w + p.off_skip;
   const double* X = (const double*)Bnew;
   const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
   const int n = p.n, Nl = p.Nl;
@@ -509,15 +543,16 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
 
   TNML_COUNT(1);
-  k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial);
-  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, (double*)svals + n, st);
+  k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial, nullptr);
+  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, (double*)svals + n, refine == 1 ? skip : nullptr, nullptr, st);
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
     TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
     TNML_COUNT(1);
-    k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial);
-    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, (double*)svals + n + 1, st);
+    k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial, refine == 1 ? skip : nullptr);
+    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, (double*)svals + n + 1, refine == 1 ? skip : nullptr, lam1,
+                  st);
     TNML_COUNT(1);
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
                                                                         k_long_stride, map_long);

@@ -317,25 +317,38 @@ class SweepEngine:
         if (not left_dir and not (0 <= l <= S - 2)) or (left_dir and not (1 <= l <= S - 1)):
             raise Exception("l = %d -> position not allowed for %s sweep step" % (l, "left" if left_dir else "right"))
         step = self.hist["n"]
-        # environment (and norm environment) advance over the site fixed by the previous step  NC:637-642 / NC:669-674
-        if not left_dir and p > 0:
-            self._advance_right(p - 1)
-            if L2_flag:
-                self._norm_step(p - 1, left_moving=False)
-        if left_dir and q < S - 1:
-            self._advance_left(q + 1)
-            if L2_flag:
-                self._norm_step(q + 1, left_moving=True)
+        main = torch.cuda.current_stream(self.device)
+        side = self._side_stream() if self.overlap_svd else main
         Dl, Dm, Dr = self.bonds[p], self.bonds[q], self.bonds[q + 1]
         nB = Dl * 4 * L * Dr
-        # B = A_p . A_q                                                                      NC:484
-        B = self._empty(nB)
-        if not left_dir:
-            call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]), 2 * Dr,
-                 0.0, _ptr(B), 2 * Dr, F64, st)
-        else:
-            call("tnml_gemm", 0, 0, Dl * 2, L * 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
-                 L * 2 * Dr, 0.0, _ptr(B), L * 2 * Dr, F64, st)
+        B, G, Bn = self._empty(nB), (self._empty(nB) if L2_flag else None), self._empty(nB)
+        # ---- batch-independent preparation on the side stream (off the critical path: none of it needs the gradient):
+        #      norm-environment advance NC:1004-1061, B = A_p . A_q NC:484, L2 derivative E_L.B.E_R NC:1129-1135
+        if side is not main:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            sst = side.cuda_stream
+            if L2_flag:
+                if not left_dir and p > 0:
+                    self._norm_step(p - 1, left_moving=False)
+                if left_dir and q < S - 1:
+                    self._norm_step(q + 1, left_moving=True)
+            if not left_dir:
+                call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
+                     2 * Dr, 0.0, _ptr(B), 2 * Dr, F64, sst)
+            else:
+                call("tnml_gemm", 0, 0, Dl * 2, L * 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
+                     L * 2 * Dr, 0.0, _ptr(B), L * 2 * Dr, F64, sst)
+            if L2_flag:
+                ws_l2 = self._workspace("l2", nB * 8)
+                call("tnml_l2_term", _ptr(B), _ptr(self.nrmL[p]), _ptr(self.nrmR[q + 1]), _ptr(G), _ptr(ws_l2), Dl, Dr, L,
+                     F64, sst)
+        # ---- critical path on the main stream
+        # environment advance over the site fixed by the previous step                       NC:637-642 / NC:669-674
+        if not left_dir and p > 0:
+            self._advance_right(p - 1)
+        if left_dir and q < S - 1:
+            self._advance_left(q + 1)
         # activation, loss derivative, metrics                                              NC:694-707
         f_in = self.f_buf[self.f_cur]
         gbuf = self._workspace("gbuf", (nB + 4) * 8)
@@ -351,13 +364,11 @@ class SweepEngine:
         reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world)   # one collective per update
         self.hist["metrics"][step].copy_(met)
         # regularisation, clipping, update                                                   NC:728-761
-        Bn = self._empty(nB)
+        if side is not main:
+            main.wait_stream(side)                      # B and G are ready
         ws = self._workspace("bu", _lib.lib().tnml_bond_update_workspace_bytes(Dl, Dr, L))
-        EL = self.nrmL[p] if L2_flag else None
-        ER = self.nrmR[q + 1] if L2_flag else None
-        call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(EL), _ptr(ER), _ptr(Bn),
-             self.hist["stats"].data_ptr() + step * 6 * 8, _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec),
-             1 if L2_flag else 0, F64, st)
+        call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 6 * 8,
+             _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec), 1 if L2_flag else 0, F64, st)
         # SVD split + truncation + label move (NC:528-563, NC:839-962) runs on a side stream, concurrently with the
         # new prediction from the UN-truncated B' (NC:494-523) on the main stream: neither depends on the other.
         R, Cc = (2 * Dl, 2 * L * Dr) if not left_dir else (2 * Dl * L, 2 * Dr)
@@ -367,8 +378,6 @@ class SweepEngine:
         ws_svd = self._workspace("svd", _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
         f_out = self.f_buf[1 - self.f_cur]
         ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
-        main = torch.cuda.current_stream(self.device)
-        side = self._side_stream() if self.overlap_svd else main
         if side is not main:
             side.wait_stream(main)                      # B' is ready
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
@@ -382,7 +391,7 @@ class SweepEngine:
                      self.svd_refine, F64, side.cuda_stream)
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
-            self._inflight = (B, Bn, dB)                # keep alive until the main stream has passed the wait
+            self._inflight = (B, Bn, dB, G)             # keep alive until the main stream has passed the wait
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     from tensornetworkforml_b200 import _lib
     header = open(os.path.join(ROOT, "include", "tnml.h")).read()
     declared = set(re.findall(r"\b(tnml_[a-z0-9_]+)\s*\(", header))
-    assert len(declared) >= 20
+    assert len(declared) >= 22
     handle = _lib.lib()
     for name in declared:
         assert hasattr(handle, name), "libtnml.so does not export %s" % name

@@ -199,8 +199,13 @@ def test_bond_update(L, Dl, Dr, nl, L2, scale):
     lr, wd = 0.05, 0.3
     Bn, stats = empty(Dl, 2, nl, 2, Dr), empty(6)
     ws = ws_for(L, "tnml_bond_update_workspace_bytes", Dl, Dr, nl)
-    L.call("tnml_bond_update", dev(B).data_ptr(), dev(dB).data_ptr(), dev(EL).data_ptr(), dev(ER).data_ptr(),
-           Bn.data_ptr(), stats.data_ptr(), ws.data_ptr(), Dl, Dr, nl, lr, wd, L2, L.F64, st())
+    Bd, Gd, ws2 = dev(B), empty(Dl, 2, nl, 2, Dr), empty(Dl * 4 * nl * Dr)
+    if L2:
+        L.call("tnml_l2_term", Bd.data_ptr(), dev(EL).data_ptr(), dev(ER).data_ptr(), Gd.data_ptr(), ws2.data_ptr(), Dl,
+               Dr, nl, L.F64, st())
+        assert rel(Gd, np.einsum("xa,asltc,cy->xslty", EL, B, ER)) < TOL
+    L.call("tnml_bond_update", Bd.data_ptr(), dev(dB).data_ptr(), Gd.data_ptr() if L2 else None, Bn.data_ptr(),
+           stats.data_ptr(), ws.data_ptr(), Dl, Dr, nl, lr, wd, L2, L.F64, st())
     if L2:
         loss, g = O.l2_term(B, EL, ER, wd)
         d = dB - g
@@ -232,7 +237,7 @@ def test_norm_env_step(L, Dl, Dr):
     assert rel(out, O.norm_env_left_step(ER, A)) < TOL
 
 
-def _run_svd(L, B, left_dir, m, refine=1):
+def _run_svd(L, B, left_dir, m, refine=2):
     Dl, _, nl, _, Dr = B.shape
     site_p = empty(Dl * 2 * m * (nl if left_dir else 1))
     site_q = empty(m * 2 * Dr * (1 if left_dir else nl))
@@ -251,7 +256,7 @@ def _run_svd(L, B, left_dir, m, refine=1):
     return sv.cpu().numpy()[:n], prod, Ap, Aq
 
 
-@pytest.mark.parametrize("refine", [1, 0])
+@pytest.mark.parametrize("refine", [2, 1, 0])
 @pytest.mark.parametrize("Dl,Dr,nl,left_dir,m", [(4, 4, 3, 0, 4), (4, 4, 3, 1, 4), (64, 64, 10, 0, 64),
                                                  (64, 64, 10, 1, 64), (1, 5, 2, 0, 2), (5, 1, 2, 1, 2), (4, 1, 2, 0, 4),
                                                  (1, 3, 2, 1, 4), (2, 2, 2, 0, 2), (7, 5, 3, 0, 9), (3, 9, 2, 1, 5)])
