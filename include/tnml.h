@@ -81,6 +81,13 @@ int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const v
                      void* metrics, void* ws, int64_t Ns, int32_t L, int32_t act, int32_t loss, double T,
                      int32_t dtype, tnml_stream_t stream);
 
+/* Standalone forms on the reference's own (L, Ns) layout, for the public methods Network.apply_act_func (NC:767-796)
+ * and Network.compute_loss_derivate (NC:800-835); y is the dense (one-hot) target the reference passes. */
+int tnml_apply_act(const void* f, void* out, int64_t Ns, int32_t L, int32_t act, double T, int32_t dtype,
+                   tnml_stream_t stream);
+int tnml_loss_derivative(const void* fa, const void* y, void* out, int64_t Ns, int32_t L, int32_t act, int32_t loss,
+                         double T, int32_t dtype, tnml_stream_t stream);
+
 /* ---- a10: gradient, a K = Ns tensor-core reduction ---------------------------------------------------
  * dB[a][sigma][l][tau][c] = sum_b q[b][l][sigma,tau] L[b][a] R[b][c]          NC:625-646 + NC:710
  * Split-K over samples with a static decomposition and a fixed-order second stage => bitwise reproducible.
@@ -136,6 +143,12 @@ int tnml_norm_env_step(const void* Ein, const void* site, void* Eout, void* ws, 
 int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
 int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
                    int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream);
+
+/* General form for Network.tensor_svd on any 2-D Tensor (NC:839-962): Mx [R][C] -> US [R][m] = U sqrt(S),
+ * SVh [m][C] = sqrt(S) Vh; svals as above (min(R,C) + 2 values). */
+int64_t tnml_svd_workspace_bytes(int32_t R, int32_t C);
+int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* ws, int32_t R, int32_t C, int32_t m, int32_t refine,
+             int32_t dtype, tnml_stream_t stream);
 
 /* ---- label-site layout change between sweep directions: [a][s][l][c] <-> [a][l][s][c] ------------------- */
 int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32_t Dr, int32_t L, int32_t to_left_layout,

@@ -261,6 +261,200 @@ class Network():
         self._last_f = out
         return out
 
+    # ------------------------------------------------------------------ update_B (NC:577-763)
+    def update_B(self, B, f_orig, y, lr, weight_dec, L2_flag=True, ldf=0, var_hist=None, debug=False):
+        """Gradient step on the bond tensor at the current label position: returns the updated B' as a Tensor with
+        B's axis names.  Like the reference it advances the environment cache of the sweep as a side effect and
+        appends the pre-update metrics to ``var_hist``.  ``y`` is the one-hot target (L, batch)."""
+        eng = self._engine()
+        if eng.phi is None:
+            raise Exception("call forward(X) before update_B: the environments of the batch are built there")
+        left_dir = bool(ldf)
+        self._push_f(f_orig)
+        y = np.asarray(y)
+        labels = np.argmax(y, axis=0) if y.ndim == 2 else y
+        first = (self.l_pos == (self.N - 1 if left_dir else 0))
+        if first or eng.hist is None:
+            eng.begin_sweep(labels, left_dir, L2_flag)
+        else:
+            eng.set_labels(labels)
+            eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+        p = self.l_pos - ldf
+        import torch
+        Bc = self._bond_to_canonical(B, p)
+        ctx = eng.update_phase(lr, weight_dec, L2_flag, left_dir,
+                               B_override=torch.from_numpy(Bc).to(eng.device))
+        torch.cuda.current_stream(eng.device).wait_stream(ctx["side"])
+        eng.hist["n"] = 1
+        eng.hist["nsv"], eng.hist["m"] = [0], [0]
+        h = eng.history()
+        if var_hist is not None:
+            if debug:
+                if not L2_flag:
+                    raise NameError("name 'L2_loss_term' is not defined")     # the reference's latent bug, NC:746
+                for row, val in enumerate((h["stats"][0, 4], h["stats"][0, 5], h["acc"][0], np.nan, h["mae"][0],
+                                           h["stats"][0, 2], np.nan)):
+                    var_hist[row].append(val)
+            else:
+                var_hist[0].append(h["acc"][0])
+                var_hist[1].append(h["mae"][0])
+        eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+        Bn = ctx["Bn"].cpu().numpy().reshape(Bc.shape)
+        return self._bond_from_canonical(Bn, B, p)
+
+    def _bond_names(self, p):
+        return ["left", "d%d" % p, "l", "d%d" % (p + 1), "right"]
+
+    def _bond_to_canonical(self, B, p):
+        """Bond Tensor (names 'left','d<p>','l','d<p+1>','right', any order, edge bonds absent) -> (Dl,2,L,2,Dr)."""
+        names = [str(n) for n in B.axes_names]
+        want = [w for w in self._bond_names(p) if w in names]
+        assert len(want) == len(names), "unexpected axes %s for the bond tensor of sites %d,%d" % (names, p, p + 1)
+        arr = np.transpose(np.asarray(B.elem, dtype=np.float64), [names.index(w) for w in want])
+        if "left" not in names:
+            arr = arr[new, ...]
+        if "right" not in names:
+            arr = arr[..., new]
+        return np.ascontiguousarray(arr)
+
+    def _bond_from_canonical(self, arr, like, p):
+        """(Dl,2,L,2,Dr) array -> Tensor with the axes (and axis order) of ``like``."""
+        names = [str(n) for n in like.axes_names]
+        full = self._bond_names(p)
+        if "right" not in names:
+            arr, full = arr[..., 0], full[:-1]
+        if "left" not in names:
+            arr, full = arr[0], full[1:]
+        return Tensor(elem=np.ascontiguousarray(np.transpose(arr, [full.index(nm) for nm in names])), axes_names=names)
+
+    # ------------------------------------------------------------------ activation / loss derivative (NC:767-835)
+    def _elementwise(self, kind, f_elem, label_axis, y=None):
+        import torch
+        from . import _lib
+        eng = self._engine()
+        moved = np.moveaxis(np.asarray(f_elem, dtype=np.float64), label_axis, 0)
+        L = moved.shape[0]
+        flat = np.ascontiguousarray(moved.reshape(L, -1))
+        Ns = flat.shape[1]
+        dev = torch.from_numpy(flat).to(eng.device)
+        out = torch.empty_like(dev)
+        st = torch.cuda.current_stream(eng.device).cuda_stream
+        if kind == "act":
+            _lib.call("tnml_apply_act", dev.data_ptr(), out.data_ptr(), Ns, L, _lib.ACT[self.act_fn], float(self.T),
+                      _lib.F64, st)
+        else:
+            yb = np.broadcast_to(np.asarray(y, dtype=np.float64), np.asarray(f_elem).shape)
+            yd = torch.from_numpy(np.ascontiguousarray(np.moveaxis(yb, label_axis, 0).reshape(L, -1))).to(eng.device)
+            _lib.call("tnml_loss_derivative", dev.data_ptr(), yd.data_ptr(), out.data_ptr(), Ns, L,
+                      _lib.ACT[self.act_fn], _lib.LOSS[self.loss_fn], float(self.T), _lib.F64, st)
+        res = out.cpu().numpy().reshape(moved.shape)
+        return np.ascontiguousarray(np.moveaxis(res, 0, label_axis))
+
+    def apply_act_func(self, f):
+        """Activation of the network output (NC:767-796): identity, sigmoid(f/T) or (un-stabilised) softmax(f/T) over
+        the label axis.  Returns a new Tensor with f's axes."""
+        if self.act_fn == 'linear':
+            return Tensor(elem=np.array(f.elem, copy=True), axes_names=f.axes_names)
+        axis = int(f.ax_to_index('l')) if self.act_fn == 'softmax' else 0
+        return Tensor(elem=self._elementwise("act", f.elem, axis), axes_names=f.axes_names)
+
+    def compute_loss_derivate(self, f, y):
+        """Derivative of the loss w.r.t. the (activated) output (NC:800-835); y is the one-hot target, f's shape."""
+        if self.loss_fn == 'cross_entropy' and self.act_fn == 'softmax':
+            print("softmax + cross entropy case")                                          # NC:827
+        return Tensor(elem=self._elementwise("loss", f.elem, 0, y=y), axes_names=f.axes_names)
+
+    # ------------------------------------------------------------------ tensor_svd (NC:839-962)
+    def tensor_svd(self, T, left_dir=False, threshold=0.999):
+        """SVD split of a 2-D Tensor with aggregated axes 'i' (rows) and 'j' (columns): returns (U sqrt(S), sqrt(S) Vh)
+        truncated to the bond chosen by the truncation rule, disaggregated like NC:918-925 / NC:953-960."""
+        if type(T) != Tensor:
+            raise TypeError("This function only support object from the class Tensor")
+        if len(T.shape) != 2:
+            raise ValueError("This function only support a 2D tensors")
+        import torch
+        from . import _lib
+        from .engine import choose_m
+        eng = self._engine()
+        R, C = T.elem.shape
+        Dl = int(T.aggregations.get('i', {}).get('left', 1))
+        m = choose_m(self._opts["truncation"], self._opts["max_bond"], bool(left_dir), self.l_pos, self.N, Dl, R, C)
+        mx = torch.from_numpy(np.ascontiguousarray(T.elem, dtype=np.float64)).to(eng.device)
+        US = torch.empty((R, m), dtype=torch.float64, device=eng.device)
+        SVh = torch.empty((m, C), dtype=torch.float64, device=eng.device)
+        sv = torch.empty(min(R, C) + 2, dtype=torch.float64, device=eng.device)
+        ws = torch.empty(max(1, _lib.lib().tnml_svd_workspace_bytes(R, C) // 8), dtype=torch.float64, device=eng.device)
+        _lib.call("tnml_svd", mx.data_ptr(), US.data_ptr(), SVh.data_ptr(), sv.data_ptr(), ws.data_ptr(), R, C, m,
+                  2 if self._opts["svd_refine"] else 0, _lib.F64, torch.cuda.current_stream(eng.device).cuda_stream)
+        self.last_singular_values = sv.cpu().numpy()[:min(R, C)]
+        TU = Tensor(elem=US.cpu().numpy(), axes_names=['i', 'right'])
+        TSVh = Tensor(elem=SVh.cpu().numpy(), axes_names=['left', 'j'])
+        TU.aggregations['i'] = T.aggregations['i']
+        TSVh.aggregations['j'] = T.aggregations['j']
+        TU.disaggregate('i')
+        TSVh.disaggregate('j')
+        return TU, TSVh
+
+    # ------------------------------------------------------------------ compute_L2_reg (NC:966-1179)
+    def compute_L2_reg(self, B, weight_dec=0.001, left_dir=False):
+        """(weight_dec * ||net||^2 restricted to B's environments, its derivative 2 weight_dec E_L.B.E_R) for the bond
+        tensor at the current label position; the norm environments are contracted from the current site tensors."""
+        import torch
+        from . import _lib
+        eng = self._engine()
+        eng._label_to("L" if left_dir else "R")
+        p = self.l_pos - int(bool(left_dir))
+        Bc = self._bond_to_canonical(B, p)
+        Dl, _, L, _, Dr = Bc.shape
+        eng._build_norm_stack(bool(left_dir))
+        # the far side is complete; contract the near side up to the pair
+        if not left_dir:
+            for s_ in range(0, p):
+                eng._norm_step(s_, left_moving=False)
+        else:
+            for s_ in range(self.N - 1, p + 1, -1):
+                eng._norm_step(s_, left_moving=True)
+        Bd = torch.from_numpy(Bc.reshape(-1)).to(eng.device)
+        G = torch.empty_like(Bd)
+        ws = torch.empty_like(Bd)
+        _lib.call("tnml_l2_term", Bd.data_ptr(), eng.nrmL[p].data_ptr(), eng.nrmR[p + 2].data_ptr(), G.data_ptr(),
+                  ws.data_ptr(), Dl, Dr, L, _lib.F64, torch.cuda.current_stream(eng.device).cuda_stream)
+        Gh = G.cpu().numpy().reshape(Bc.shape)
+        loss_term = float(weight_dec * np.sum(Bc * Gh))
+        return loss_term, self._bond_from_canonical(2 * weight_dec * Gh, B, p)
+
+    # ------------------------------------------------------------------ cached batch (NC:37-47)
+    @property
+    def TX(self):
+        """The last input batch as the reference's list of (batch, d_i) Tensors (NC:222-225), read from the device."""
+        eng = self._eng
+        if eng is None or eng.phi is None:
+            return []
+        phi = eng.phi.view(self.N, eng.Ns, 2).cpu().numpy()
+        return [Tensor(elem=phi[i], axes_names=['b', 'd' + str(i)]) for i in range(self.N)]
+
+    def _cum(self, right):
+        eng = self._eng
+        if eng is None or eng.env is None or self._last_f is None:
+            return None
+        if (right and self.l_pos != 0) or (not right and self.l_pos != self.N - 1):
+            return None
+        Ns, S = eng.Ns, self.N
+        envs = [eng.env[p, :Ns * eng.bonds[p]].view(Ns, eng.bonds[p]).t().cpu().numpy() for p in range(S + 1)]
+        if right:   # r_cum_contraction[i] = sites i..S-1 contracted with the input: ('left', 'b'); [0] is the output
+            return [self._last_f] + [Tensor(elem=envs[p], axes_names=['left', 'b']) for p in range(1, S)]
+        return [Tensor(elem=envs[p + 1], axes_names=['right', 'b']) for p in range(S - 1)] + [self._last_f]
+
+    @property
+    def r_cum_contraction(self):
+        """Right cumulative contractions of the last forward (NC:231-242); None unless the label sits at site 0."""
+        return self._cum(True)
+
+    @property
+    def l_cum_contraction(self):
+        """Left cumulative contractions of the last forward (NC:244-255); None unless the label sits at site N-1."""
+        return self._cum(False)
+
     # ------------------------------------------------------------------ pickle layout (SURVEY.md section 5)
     def __getstate__(self):
         As = self.As

@@ -27,6 +27,8 @@ SIGNATURES = {
     "tnml_site_predict": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tnml_act_lossder_workspace_bytes": (_i64, [_i64]),
     "tnml_act_lossder": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _f64, _i32, _vp]),
+    "tnml_apply_act": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f64, _i32, _vp]),
+    "tnml_loss_derivative": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _f64, _i32, _vp]),
     "tnml_grad_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "tnml_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tnml_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _i32, _f64, _vp, _i32, _i32, _vp]),
@@ -38,6 +40,8 @@ SIGNATURES = {
     "tnml_norm_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tnml_svd_split_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "tnml_svd_split": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_svd_workspace_bytes": (_i64, [_i32, _i32]),
+    "tnml_svd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_label_site_swap": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_contract": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
 }

@@ -66,6 +66,39 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
   }
 }
 
+// Standalone activation on the reference's own layout f[l][b] (L x Ns), one thread per sample.   NC:767-796
+__global__ void __launch_bounds__(256) k_apply_act(const double* __restrict__ f, double* __restrict__ out, int64_t Ns,
+                                                   int L, int act, double T) {
+  const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (b >= Ns) return;
+  double denom = 1.0;
+  if (act == TNML_ACT_SOFTMAX) {
+    denom = 0.0;
+    for (int l = 0; l < L; ++l) denom += exp(f[(int64_t)l * Ns + b] / T);
+  }
+  for (int l = 0; l < L; ++l) {
+    const double v = f[(int64_t)l * Ns + b];
+    double fa;
+    if (act == TNML_ACT_LINEAR) fa = v;
+    else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));
+    else fa = exp(v / T) / denom;
+    out[(int64_t)l * Ns + b] = fa;
+  }
+}
+
+// Standalone loss derivative, dense target y[l][b] (the reference takes a one-hot float array).   NC:800-835
+__global__ void __launch_bounds__(256) k_loss_der(const double* __restrict__ fa, const double* __restrict__ y,
+                                                  double* __restrict__ out, int64_t n, int act, int loss, double T) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  const double f = fa[e], yy = y[e];
+  double g;
+  if (loss == TNML_LOSS_MSE) g = yy - f;
+  else if (loss == TNML_LOSS_CROSS_ENTROPY) g = (act == TNML_ACT_SOFTMAX) ? (yy - yy * f) / T : yy / f;
+  else g = 1.0 / ((yy == 0.0 ? f - 1.0 : f) + 1e-4);
+  out[e] = g;
+}
+
 // fixed-order final sum of the per-block partials (one block)
 __global__ void __launch_bounds__(256) k_metrics_final(const double* __restrict__ partial, int nblocks,
                                                       double* __restrict__ metrics) {
@@ -244,6 +277,25 @@ extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi
                                                             Ns, L, act, loss, T);
   TNML_COUNT(1);
   k_metrics_final<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)ws, nb, (double*)metrics);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_apply_act(const void* f, void* out, int64_t Ns, int32_t L, int32_t act, double T, int32_t dtype,
+                              tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(f && out && Ns > 0 && L > 0 && act >= 0 && act <= 2);
+  TNML_COUNT(1);
+  k_apply_act<<<tnml_cdiv(Ns, 256), 256, 0, (cudaStream_t)stream>>>((const double*)f, (double*)out, Ns, L, act, T);
+  return tnml_launch_status();
+}
+
+extern "C" int tnml_loss_derivative(const void* fa, const void* y, void* out, int64_t Ns, int32_t L, int32_t act,
+                                    int32_t loss, double T, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(fa && y && out && Ns > 0 && L > 0 && act >= 0 && act <= 2 && loss >= 0 && loss <= 2);
+  TNML_COUNT(1);
+  k_loss_der<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>((const double*)fa, (const double*)y, (double*)out,
+                                                                      Ns * L, act, loss, T);
   return tnml_launch_status();
 }
 

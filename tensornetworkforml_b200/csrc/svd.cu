@@ -473,10 +473,59 @@ struct SvdPlan {
   size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, total;
 };
 
+static SvdPlan svd_plan_rc(int R, int C);
 static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
+  return svd_plan_rc(left_dir ? 2 * Dl * L : 2 * Dl, left_dir ? 2 * Dr : 2 * L * Dr);
+}
+
+// Shared implementation: X = R x C row-major matrix, rowmap/colmap = where row i / column j of the factors land.
+static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_rows, Idx3 rowmap, long long row_k,
+                    double* dst_cols, Idx3 colmap, long long col_k, double* svals, double* w, cudaStream_t st) {
+  if (p.n > SVD_MAXN) return TNML_ERR_UNSUPPORTED;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = jacobi_prepare();
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    e = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * (SVD_MAXN + 1) + SVD_MAXN * 33) * 8);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    attr_set = true;
+  }
+  double *partial = w + p.off_partial, *vt1 = w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
+         *lam2 = w + p.off_lam2, *Y = w + p.off_Y, *skip = w + p.off_skip;
+  const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
+  const int n = p.n, Nl = p.Nl;
+  const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
+  const size_t rsmem = (size_t)(32 * (n + 1) + n * 33) * 8;
+  double* dst_short = p.rows_short ? dst_rows : dst_cols;
+  double* dst_long = p.rows_short ? dst_cols : dst_rows;
+  const Idx3 map_short = p.rows_short ? rowmap : colmap, map_long = p.rows_short ? colmap : rowmap;
+  const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
+
+  TNML_COUNT(1);
+  k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial, nullptr);
+  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, svals + n, refine == 1 ? skip : nullptr, nullptr, st);
+  if (refine) {
+    const Idx3 dense{1, 1, 1, 0, 0};
+    TNML_COUNT(4);
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
+    k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial, refine == 1 ? skip : nullptr);
+    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, svals + n + 1, refine == 1 ? skip : nullptr, lam1, st);
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
+                                                                        k_long_stride, map_long);
+    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short, svals);
+  } else {
+    TNML_COUNT(2);
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
+                                                                        k_long_stride, map_long);
+    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short, svals);
+  }
+  return tnml_launch_status();
+}
+
+static SvdPlan svd_plan_rc(int R, int C) {
   SvdPlan p;
-  p.R = left_dir ? 2 * Dl * L : 2 * Dl;
-  p.C = left_dir ? 2 * Dr : 2 * L * Dr;
+  p.R = R;
+  p.C = C;
   p.rows_short = p.R <= p.C;
   p.n = p.rows_short ? p.R : p.C;
   p.Nl = p.rows_short ? p.C : p.R;
@@ -508,25 +557,6 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   TNML_REQUIRE(Bnew && site_p && site_q && svals && ws && Dl > 0 && Dr > 0 && L > 0);
   SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
   TNML_REQUIRE(m > 0 && m <= p.n);
-  if (p.n > SVD_MAXN) return TNML_ERR_UNSUPPORTED;
-  cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = jacobi_prepare();
-    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    e = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * (SVD_MAXN + 1) + SVD_MAXN * 33) * 8);
-    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    attr_set = true;
-  }
-  double* w = (double*)ws;
-  double *partial = w + p.off_partial, *vt1 = w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
-         *lam2 = w + p.off_lam2, *Y = w + p.off_Y, *skip = w + p.off_skip;
-  const double* X = (const double*)Bnew;
-  const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
-  const int n = p.n, Nl = p.Nl;
-  const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
-  const size_t rsmem = (size_t)(32 * (n + 1) + n * 33) * 8;
-
   // destination maps (see tnml.h): rows of Mx -> site_p, columns of Mx -> site_q
   Idx3 rowmap, colmap;
   long long row_k, col_k;
@@ -537,35 +567,20 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
     rowmap = Idx3{2, L, (long long)L * 2 * m, (long long)m, 2LL * m}; row_k = 1;          // site_p[a][l][s][k]
     colmap = Idx3{1, 1, 1, 0, 0}; col_k = 2LL * Dr;                                       // site_q[k][t][c]
   }
-  double* dst_short = (double*)(p.rows_short ? site_p : site_q);
-  double* dst_long = (double*)(p.rows_short ? site_q : site_p);
-  const Idx3 map_short = p.rows_short ? rowmap : colmap, map_long = p.rows_short ? colmap : rowmap;
-  const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
+  return svd_core((const double*)Bnew, p, m, refine, (double*)site_p, rowmap, row_k, (double*)site_q, colmap, col_k,
+                  (double*)svals, (double*)ws, (cudaStream_t)stream);
+}
 
-  TNML_COUNT(1);
-  k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial, nullptr);
-  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, (double*)svals + n, refine == 1 ? skip : nullptr, nullptr, st);
-  if (refine) {
-    const Idx3 dense{1, 1, 1, 0, 0};
-    TNML_COUNT(1);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
-    TNML_COUNT(1);
-    k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial, refine == 1 ? skip : nullptr);
-    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, (double*)svals + n + 1, refine == 1 ? skip : nullptr, lam1,
-                  st);
-    TNML_COUNT(1);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
-                                                                        k_long_stride, map_long);
-    TNML_COUNT(1);
-    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short,
-                                                   (double*)svals);
-  } else {
-    TNML_COUNT(1);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
-                                                                        k_long_stride, map_long);
-    TNML_COUNT(1);
-    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short,
-                                                   (double*)svals);
-  }
-  return tnml_launch_status();
+extern "C" int64_t tnml_svd_workspace_bytes(int32_t R, int32_t C) { return (int64_t)svd_plan_rc(R, C).total * 8; }
+
+extern "C" int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* ws, int32_t R, int32_t C, int32_t m,
+                        int32_t refine, int32_t dtype, tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(Mx && US && SVh && svals && ws && R > 0 && C > 0);
+  SvdPlan p = svd_plan_rc(R, C);
+  TNML_REQUIRE(m > 0 && m <= p.n);
+  const Idx3 rowmap{1, 1, (long long)m, 0, 0};   // US[i][k]
+  const Idx3 colmap{1, 1, 1, 0, 0};              // SVh[k][j]
+  return svd_core((const double*)Mx, p, m, refine, (double*)US, rowmap, 1, (double*)SVh, colmap, C, (double*)svals,
+                  (double*)ws, (cudaStream_t)stream);
 }

@@ -24,6 +24,35 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def choose_m(rule, max_bond, left_dir, l_pos, S, Dl, R, C):
+    """Bond kept by the SVD split.  'fixed': min(len(S), max_bond).  'reference': NC:898-910 / NC:933-945 -- the left
+    bond of the pair in the interior, len(S) at the chain ends; raises where the reference's np.dot would."""
+    nS = min(R, C)
+    if rule == "fixed":
+        return min(nS, max_bond)
+    if not left_dir:
+        if l_pos == 0:
+            return nS                                    # NC:898-901
+        if l_pos < S - 2:
+            if Dl > nS:
+                raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
+            return Dl                                    # NC:902-906
+        if C != nS:                                      # NC:907-910: Vh stays (C,C), np.dot(Sqrt, Vh) fails
+            raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
+        return nS
+    if l_pos == S - 1:
+        if C != nS:                                      # NC:933-936
+            raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
+        return nS
+    if l_pos > 1:
+        if Dl > nS:
+            raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
+        return Dl                                        # NC:937-941
+    if R != nS:                                          # NC:942-945: U stays (R,R), np.dot(U, Sqrt) fails
+        raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (R, R, nS, nS))
+    return nS
+
+
 class _Timed:
     """Optional CUDA-event bracket around one C-ABI call (bench.py's live per-kernel timing)."""
 
@@ -241,31 +270,7 @@ class SweepEngine:
         assert self.y_dev.numel() == self.Ns
 
     def _choose_m(self, left_dir, Dl, R, C):
-        nS = min(R, C)
-        if self.rule == "fixed":
-            return min(nS, self.max_bond)
-        l, S = self.l_pos, self.S
-        if not left_dir:
-            if l == 0:
-                return nS                                    # NC:898-901
-            if l < S - 2:
-                if Dl > nS:
-                    raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
-                return Dl                                    # NC:902-906
-            if C != nS:                                      # NC:907-910: Vh stays (C,C), np.dot(Sqrt, Vh) fails
-                raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
-            return nS
-        if l == S - 1:
-            if C != nS:                                      # NC:933-936
-                raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (nS, nS, C, C))
-            return nS
-        if l > 1:
-            if Dl > nS:
-                raise ValueError("reference rule: left bond %d exceeds len(S)=%d" % (Dl, nS))
-            return Dl                                        # NC:937-941
-        if R != nS:                                          # NC:942-945: U stays (R,R), np.dot(U, Sqrt) fails
-            raise ValueError("shapes (%d,%d) and (%d,%d) not aligned" % (R, R, nS, nS))
-        return nS
+        return choose_m(self.rule, self.max_bond, left_dir, self.l_pos, self.S, Dl, R, C)
 
     def _build_norm_stack(self, left_dir):
         S = self.S
@@ -310,6 +315,12 @@ class SweepEngine:
 
     def sweep_step(self, lr, weight_dec, L2_flag, left_dir):
         """One bond update (NC:440-573 with update_B NC:577-763); everything stays on the device."""
+        ctx = self.update_phase(lr, weight_dec, L2_flag, left_dir)
+        return self.split_phase(ctx)
+
+    def update_phase(self, lr, weight_dec, L2_flag, left_dir, B_override=None):
+        """update_B (NC:577-763): environment advance, loss derivative + metrics, gradient, regularisation, clipping,
+        update.  Returns the context the split phase needs; ctx["Bn"] is the updated bond tensor B'."""
         S, L, Ns, st = self.S, self.L, self.Ns, self._stream()
         l = self.l_pos
         p = l - 1 if left_dir else l
@@ -333,7 +344,9 @@ class SweepEngine:
                     self._norm_step(p - 1, left_moving=False)
                 if left_dir and q < S - 1:
                     self._norm_step(q + 1, left_moving=True)
-            if not left_dir:
+            if B_override is not None:
+                B.copy_(B_override.reshape(-1))
+            elif not left_dir:
                 call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
                      2 * Dr, 0.0, _ptr(B), 2 * Dr, F64, sst)
             else:
@@ -369,8 +382,15 @@ class SweepEngine:
         ws = self._workspace("bu", _lib.lib().tnml_bond_update_workspace_bytes(Dl, Dr, L))
         call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 6 * 8,
              _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec), 1 if L2_flag else 0, F64, st)
-        # SVD split + truncation + label move (NC:528-563, NC:839-962) runs on a side stream, concurrently with the
-        # new prediction from the UN-truncated B' (NC:494-523) on the main stream: neither depends on the other.
+        self._inflight = (B, Bn, dB, G)
+        return dict(B=B, Bn=Bn, p=p, q=q, Dl=Dl, Dr=Dr, nB=nB, left_dir=left_dir, step=step, main=main, side=side)
+
+    def split_phase(self, ctx):
+        """New prediction from the UN-truncated B' (NC:494-523) on the main stream, concurrently with the SVD split +
+        truncation + label move (NC:528-563, NC:839-962) on a side stream: neither depends on the other."""
+        S, L, Ns, st = self.S, self.L, self.Ns, self._stream()
+        Bn, p, q, Dl, Dr, left_dir, step = (ctx[k] for k in ("Bn", "p", "q", "Dl", "Dr", "left_dir", "step"))
+        main, side = ctx["main"], ctx["side"]
         R, Cc = (2 * Dl, 2 * L * Dr) if not left_dir else (2 * Dl * L, 2 * Dr)
         m = self._choose_m(left_dir, Dl, R, Cc)
         new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
@@ -391,7 +411,7 @@ class SweepEngine:
                      self.svd_refine, F64, side.cuda_stream)
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
-            self._inflight = (B, Bn, dB, G)             # keep alive until the main stream has passed the wait
+            self._inflight = (self._inflight, ctx)      # keep alive until the main stream has passed the wait
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

@@ -200,3 +200,95 @@ def test_errors_match_reference_conventions(tn):
     X = O.feature_map(np.random.random((16, 6)))
     with pytest.raises(ValueError, match="not aligned"):
         net3.sweep(X, np.random.randint(0, 3, 16), net3.forward(X), 0.01, 0.0, L2_flag=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the remaining public methods of the reference class, called on their own
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("act", O.ACT_FNS)
+@pytest.mark.parametrize("loss", O.LOSS_FNS)
+def test_apply_act_func_and_compute_loss_derivate(tn, act, loss):
+    np.random.seed(2)
+    net = tn.Network(N=4, M=2, L=5, T=0.1, act_fn=act, loss_fn=loss)
+    f = np.random.random((5, 37)) * 0.3 + 0.05
+    y = np.eye(5)[np.random.randint(0, 5, 37)].T
+    T = tn.Tensor(elem=f.copy(), axes_names=['l', 'b'])
+    with quiet():
+        fa = net.apply_act_func(T)
+        g = net.compute_loss_derivate(fa, y)
+    want_fa = O.apply_act(f.T, act, 0.1)
+    want_g = O.loss_derivative(want_fa, y.T, act, loss, 0.1)
+    assert list(fa.axes_names) == ['l', 'b'] and np.array_equal(T.elem, f)       # input untouched, like the deepcopy
+    assert G.rel(fa.elem.T, want_fa) < 1e-14 and G.rel(g.elem.T, want_g) < 1e-13
+
+
+def _seeded_pair(tn, S=8, Ns=96, Lbl=3, D=4, rule="fixed", act="linear", loss="MSE"):
+    np.random.seed(9)
+    X = O.feature_map(np.random.random((Ns, S)))
+    y = np.random.randint(0, Lbl, Ns)
+    state = np.random.get_state()
+    mb = D if rule == "fixed" else None
+    orc = O.OracleMPS.from_seed(S, D, Lbl, calibration_X=X, normalize=True, act_fn=act, loss_fn=loss, rule=rule, max_bond=mb)
+    np.random.set_state(state)
+    with quiet():
+        net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn=act, loss_fn=loss, truncation=rule,
+                         max_bond=mb)
+    return net, orc, X, y
+
+
+def test_update_B_compute_L2_reg_and_tensor_svd_standalone(tn):
+    """Re-enact one reference sweep_step (NC:484-563) with the public pieces: contract, update_B, compute_L2_reg,
+    aggregate + tensor_svd -- and compare every intermediate with the oracle."""
+    lr, wd = 0.05, 0.3
+    net, orc, X, y = _seeded_pair(tn)
+    S, Lbl = net.N, net.L
+    f = net.forward(X)
+    fo = orc.forward(X)
+    y1h = np.eye(Lbl)[y]
+    # oracle intermediates at l_pos = 0 (pair 0,1)
+    orc._build_norm_stack(False)
+    B_o = np.einsum("aslm,mtc->asltc", orc.sites[0], orc.sites[1])
+    g = O.loss_derivative(O.apply_act(fo, "linear", 0.1), y1h, "linear", "MSE", 0.1)
+    dB = O.gradient(g, orc.env[0], X[:, 0], X[:, 1], orc.env[2])
+    l2_loss, l2_grad = O.l2_term(B_o, orc._norm[0], orc._norm[2], wd)
+    Bn_o = O.clip_and_update(B_o, dB - l2_grad, lr)
+    # ours
+    As = net.As
+    B = tn.contract(As[0], As[1], "right", "left")                                  # NC:484
+    assert G.rel(net._bond_to_canonical(B, 0), B_o) < 1e-13
+    loss_term, der = net.compute_L2_reg(B, wd, False)                                # NC:729
+    assert abs(loss_term - l2_loss) < 1e-12 * abs(l2_loss)
+    assert sorted(map(str, der.axes_names)) == sorted(map(str, B.axes_names))
+    assert G.rel(net._bond_to_canonical(der, 0), l2_grad) < 1e-12
+    vh = [[], []]
+    Bn = net.update_B(B, f, y1h.T, lr, wd, L2_flag=True, ldf=0, var_hist=vh)         # NC:487
+    assert G.rel(net._bond_to_canonical(Bn, 0), Bn_o) < 1e-12
+    acc, mae = O.metrics(fo, y1h)
+    assert abs(vh[0][0] - acc) < 1e-14 and abs(vh[1][0] - mae) < 1e-13
+    # aggregate like NC:530-533 and split
+    Bn.aggregate(axes_names=['d0'], new_ax_name='i')
+    Bn.aggregate(axes_names=['d1', 'right', 'l'], new_ax_name='j')
+    Bn.transpose(['i', 'j'])
+    Mx = Bn.elem.copy()
+    TU, TSVh = net.tensor_svd(Bn, False)
+    assert list(TU.axes_names) == ['d0', 'right'] and list(TSVh.axes_names) == ['d1', 'right', 'l', 'left']
+    U, Sv, Vh = np.linalg.svd(Mx, full_matrices=False)
+    m = TU.elem.shape[-1]
+    assert m == 2 and np.abs(net.last_singular_values - Sv).max() / Sv.max() < 1e-12
+    prod = TU.elem @ TSVh.elem.reshape(-1, m).T
+    assert G.rel(prod, (U[:, :m] * Sv[:m]) @ Vh[:m]) < 1e-11
+    with pytest.raises(TypeError):
+        net.tensor_svd(Mx)
+    with pytest.raises(ValueError):
+        net.tensor_svd(tn.Tensor(elem=np.zeros((2, 2, 2)), axes_names=['a', 'b', 'c']))
+
+
+def test_cached_batch_attributes(tn):
+    net, orc, X, y = _seeded_pair(tn, S=6, Ns=20)
+    f = net.forward(X)
+    orc.forward(X)
+    TX = net.TX
+    assert len(TX) == 6 and list(TX[3].axes_names) == ['b', 'd3'] and np.array_equal(TX[3].elem, X[:, 3, :])
+    r = net.r_cum_contraction
+    assert net.l_cum_contraction is None and len(r) == 6 and r[0] is f
+    assert list(r[2].axes_names) == ['left', 'b'] and G.rel(r[2].elem.T, orc.env[2]) < 1e-13
