@@ -206,10 +206,18 @@ def main():
         for _ in range(S - 1):
             eng.sweep_step(c["lr"], c["wd"], c["L2"], left)
 
+    api_t = dict(forward=0.0, sweep=0.0, n=0)
+
     def api_step():
+        t0 = time.perf_counter()
         f = net.forward(X)
+        t1 = time.perf_counter()
         left = net.l_pos == S - 1
-        return net.sweep(X, y, f, c["lr"], c["wd"], L2_flag=c["L2"], left_dir=left)
+        out = net.sweep(X, y, f, c["lr"], c["wd"], L2_flag=c["L2"], left_dir=left)
+        api_t["forward"] += t1 - t0
+        api_t["sweep"] += time.perf_counter() - t1
+        api_t["n"] += 1
+        return out
 
     # ---- device-resident arm ------------------------------------------------------------------
     eng.load_input(X)
@@ -238,6 +246,13 @@ def main():
     value = n_updates / (ms * 1e-3)
     hist = eng.history()
     finite = bool(np.isfinite(hist["mae"]).all())
+    sv_raw = eng.hist["svals"][:eng.hist["n"]].cpu().numpy()
+    nsv = eng.hist["nsv"]
+    jac = np.array([[sv_raw[i, nsv[i]], sv_raw[i, nsv[i] + 1]] for i in range(len(nsv)) if nsv[i] == 2 * D])
+    jacobi_sweeps = dict(pass1_mean=float(np.nanmean(jac[:, 0])), pass1_max=float(np.nanmax(jac[:, 0])),
+                         pass2_mean=float(np.nanmean(jac[:, 1])), pass2_max=float(np.nanmax(jac[:, 1]))) if len(jac) else None
+    smin = np.array([hist["svals"][i][-1] / hist["svals"][i][0] for i in range(len(nsv)) if nsv[i] == 2 * D])
+    spectrum = dict(sigma_min_over_max_median=float(np.median(smin)), sigma_min_over_max_min=float(smin.min())) if len(smin) else None
 
     # ---- per-kernel live timing -> roofline --------------------------------------------------------
     kern = {}
@@ -267,6 +282,7 @@ def main():
     for _ in range(max(1, min(args.warmup, 2))):
         api_step()
     barrier()
+    api_t.update(forward=0.0, sweep=0.0, n=0)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -280,7 +296,8 @@ def main():
     e2e_ms = float(t.item())
     e2e = dict(value=n_updates / (e2e_ms * 1e-3), unit="bond-updates/s", h2d_bytes_per_step=int(X.nbytes + y.size * 4),
                d2h_bytes_per_step=int(f_host.elem.nbytes + (S - 1) * (4 + 6 + 4 * D) * 8),
-               ms_per_step=e2e_ms / args.steps, api="Network.forward(X_host) + Network.sweep(X_host, y_host, f)")
+               ms_per_step=e2e_ms / args.steps, api="Network.forward(X_host) + Network.sweep(X_host, y_host, f)",
+               forward_ms=api_t["forward"] / max(1, api_t["n"]) * 1e3, sweep_ms=api_t["sweep"] / max(1, api_t["n"]) * 1e3)
 
     line = dict(metric="bond_updates_per_s", value=value, unit="bond-updates/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps, s_per_sweep=ms / args.steps * 1e-3,
@@ -291,7 +308,7 @@ def main():
                                      % world, l2_flush="inputs exceed L2 (env cache %.1f GB per GPU)" %
                                      (eng.env.numel() * 8 / 1e9), bond_updates_per_step=S - 1),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, kernels=kern,
-                finite=finite, bonds_mid=eng.bond_dims()[S // 2])
+                finite=finite, bonds_mid=eng.bond_dims()[S // 2], jacobi_sweeps=jacobi_sweeps, spectrum=spectrum)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = cpu_bond_updates(1, 3, Ns, D, L, c["lr"], c["wd"], c["act"], c["loss"])
         per = float(np.mean(times))

@@ -10,9 +10,13 @@
 //             single Gram pass loses (it squares the condition number)
 //   rows      long factor  = S^-1/2 U^T Mx   = sqrt(S) Vh      written into the destination site layout
 //   short     short factor = U sqrt(S)                         written into the destination site layout
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tnml {
 
@@ -24,17 +28,26 @@ struct Idx3 {  // i -> (i / (n2*n3)) * s1 + ((i / n3) % n2) * s2 + (i % n3) * s3
   }
 };
 
-constexpr int SVD_MAXN = 128;
-constexpr int GRAM_LC = 32;  // long-side columns per CTA
+constexpr int SVD_MAXN = 512;   // short side of the matrix: 2 * bond dimension, up to D = 256
+constexpr int GRAM_TILE = 128;
 
 // partial[blk][i*n + j] = sum_{l in chunk} In(i,l) In(j,l),  In(s,l) = X[s*ss + l*sl]
+// grid = (long-side chunks, row tiles, column tiles); each CTA produces one 128 x 128 tile of its chunk's partial.
 __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long long ss, long long sl, int n, int Nl,
-                                              double* __restrict__ partial, const double* __restrict__ skip_flag) {
-  __shared__ double V[16][SVD_MAXN + 1];
-  if (skip_flag && *skip_flag != 0.0) return;   // second pass not needed (see k_jacobi)
+                                              int lc, double* __restrict__ partial, const double* __restrict__ skip_flag,
+                                              const int* __restrict__ sub) {
+  __shared__ double Va[16][GRAM_TILE + 1], Vb[16][GRAM_TILE + 1];
+  if (skip_flag && *skip_flag != 0.0) return;   // second pass not needed (see k_jacobi_finish)
+  if (sub) {                                    // second pass on the block of small singular values only
+    n = sub[0];
+    X += (long long)sub[1] * ss;
+    if (n == 0 || blockIdx.y * GRAM_TILE >= n || blockIdx.z * GRAM_TILE >= n) return;
+  }
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int l0 = blockIdx.x * GRAM_LC;
-  const int lend = min(Nl, l0 + GRAM_LC);
+  const int l0 = blockIdx.x * lc;
+  const int lend = min(Nl, l0 + lc);
+  const int r0 = blockIdx.y * GRAM_TILE, c0 = blockIdx.z * GRAM_TILE;
+  const bool diag_tile = r0 == c0;
   double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -42,19 +55,23 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
   for (int lb = l0; lb < lend; lb += 16) {
     __syncthreads();
-    for (int e = tid; e < 16 * SVD_MAXN; e += 256) {
+    for (int e = tid; e < 16 * GRAM_TILE; e += 256) {
       int lj, s;
-      if (sl == 1) { lj = e & 15; s = e >> 4; } else { s = e & (SVD_MAXN - 1); lj = e >> 7; }
-      double v = 0.0;
-      if (s < n && lb + lj < lend) v = X[(long long)s * ss + (long long)(lb + lj) * sl];
-      V[lj][s] = v;
+      if (sl == 1) { lj = e & 15; s = e >> 4; } else { s = e & (GRAM_TILE - 1); lj = e >> 7; }
+      const bool lok = lb + lj < lend;
+      double va = 0.0, vb = 0.0;
+      if (lok && r0 + s < n) va = X[(long long)(r0 + s) * ss + (long long)(lb + lj) * sl];
+      if (diag_tile) vb = va;
+      else if (lok && c0 + s < n) vb = X[(long long)(c0 + s) * ss + (long long)(lb + lj) * sl];
+      Va[lj][s] = va;
+      Vb[lj][s] = vb;
     }
     __syncthreads();
 #pragma unroll 4
     for (int lj = 0; lj < 16; ++lj) {
       double a[8], b[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] = V[lj][ty + 16 * i]; b[i] = V[lj][tx + 16 * i]; }
+      for (int i = 0; i < 8; ++i) { a[i] = Va[lj][ty + 16 * i]; b[i] = Vb[lj][tx + 16 * i]; }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -64,29 +81,16 @@ __global__ void __launch_bounds__(256) k_gram(const double* __restrict__ X, long
   double* out = partial + (size_t)blockIdx.x * n * n;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    int r = ty + 16 * i;
+    int r = r0 + ty + 16 * i;
     if (r >= n) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      int c = tx + 16 * j;
-      if (c < n) out[r * n + c] = acc[i][j];
+      int c = c0 + tx + 16 * j;
+      if (c < n) out[(size_t)r * n + c] = acc[i][j];
     }
   }
 }
 
-// One-sided (Hestenes) Jacobi on the rows of the symmetric PSD matrix G (n x n) held in shared memory, zero-padded
-// to the compile-time size NP (32, 64 or 128; a zero row never rotates).  One CTA of 8*NP threads; each HALF-warp
-// owns one row pair per round (NP/2 pairs per round), a lane holds NP/16 elements of each row as double2 vectors.
-// Per round and pair: one dot product (the squared row norms are cached, updated by the rotation and refreshed
-// once per sweep), a branch-free rotation-parameter evaluation (tan in single precision after a power-of-two
-// rescale, then c = rsqrt(1 + t^2), s = c t in double: the rotation is orthogonal to double precision whatever
-// the accuracy of t, which only affects the convergence rate), and the rotation itself.  The kernel is bound by
-// instruction issue, so everything is unrolled at compile time and the round-robin schedule is incremental.
-// Preconditioning (Drmac-Veselic): before the sweeps G is replaced in place by its diagonally pivoted Cholesky
-// factor, G = sum_k r_k r_k^T (row r_k stored in the physical row of its pivot, so no permutation is ever applied).
-// Orthogonalising the rows of R instead of the rows of G works on the spectrum sigma instead of sigma^2 and needs
-// about half the sweeps; the rows converge to sigma_k v_k^T with v_k the eigenvectors of G.
-// Output: Vt[k][:] = k-th eigenvector (unit), lam[k] = k-th eigenvalue, descending; info[0] = sweeps used.
 __device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no slow path
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -112,50 +116,73 @@ __device__ __forceinline__ void warp_sum4(double& g0, double& g1, double& g2, do
   g3 = __shfl_sync(0xffffffffu, v, 24);
 }
 
-// Four independent row-pair rotations held in registers: rows x[i], y[i] (E elements per lane), cached squared
+// Two values over the warp, both sums on every lane: 7 double shuffles instead of 10.
+__device__ __forceinline__ void warp_sum2(double& g0, double& g1, int lane) {
+  const bool hi = lane & 16;
+  double v = hi ? g1 : g0;
+  v += __shfl_xor_sync(0xffffffffu, hi ? g0 : g1, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  g0 = __shfl_sync(0xffffffffu, v, 0);
+  g1 = __shfl_sync(0xffffffffu, v, 16);
+}
+
+// NR (2 or 4) independent row-pair rotations held in registers: rows x[i], y[i] (E elements per lane), cached squared
 // norms nx[i], ny[i].  Returns true if any pair had a relative inner product above 1e-8 (a "large" rotation).
-template <int E>
-__device__ __forceinline__ bool rotate4(double (&x)[4][E], double (&y)[4][E], double (&nx)[4], double (&ny)[4],
+template <int NR, int E>
+__device__ __forceinline__ bool rotateN(double (&x)[NR][E], double (&y)[NR][E], double (&nx)[NR], double (&ny)[NR],
                                         double tol2, int lane) {
-  double g[4];
+  static_assert(NR == 2 || NR == 4, "2 or 4 rotations per set");
+  double g[NR];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double acc = 0.0;
+  for (int i = 0; i < NR; ++i) {
+    double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-    for (int k = 0; k < E; ++k) acc = fma(x[i][k], y[i][k], acc);
-    g[i] = acc;
+    for (int k = 0; k < E; ++k) {
+      if (k & 1) a1 = fma(x[i][k], y[i][k], a1);
+      else a0 = fma(x[i][k], y[i][k], a0);
+    }
+    g[i] = a0 + a1;
   }
-  warp_sum4(g[0], g[1], g[2], g[3], lane);
+  if constexpr (NR == 4) warp_sum4(g[0], g[1], g[2], g[3], lane);
+  else warp_sum2(g[0], g[1], lane);
+  // Branch-free on purpose: a data-dependent branch around each rotation would serialise the NR dependency chains
+  // (each ~25 dependent operations); with selects the compiler interleaves them.
+  double cs[NR], sn[NR];
   bool any = false;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NR; ++i) {
     const double al = nx[i], be = ny[i], ga = g[i];
     const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
     const double g2 = ga * ga, ab = al * be;
-    if (g2 > tol2 * ab && ex > 0 && ex < 2040) {
-      const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
-      // tan, cos, sin in single precision: t = 2ga / (de + sign(de) sqrt(de^2 + 4ga^2)), |t| <= 1
-      const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
-      const float hh = fmaf(df, df, tf * tf);                      // in [~1e-30, 8]: no range issues
-      const float h = hh * rsqrt_approx(hh);                       // sqrt via MUFU.RSQ
-      const float t0 = __fdividef(tf, df + copysignf(h, df));
-      const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
-      double cs = (double)cf, sn = (double)(cf * t0);
-      // exact renormalisation in double: nu = (cs^2 + sn^2)^(-1/2) = 1 - e/2 + 3e^2/8, e ~ 1e-7 -> error ~ e^3
-      const double e = fma(cs, cs, fma(sn, sn, -1.0));
-      const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
-      cs *= nu;
-      sn *= nu;
+    const bool rot = (g2 > tol2 * ab) && ex > 0 && ex < 2040;
+    const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
+    // tan, cos, sin in single precision: t = 2ga / (de + sign(de) sqrt(de^2 + 4ga^2)), |t| <= 1
+    const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
+    const float hh = fmaf(df, df, tf * tf);
+    const float h = hh * rsqrt_approx(hh);                       // sqrt via MUFU.RSQ
+    const float t0 = __fdividef(tf, df + copysignf(h, df));
+    const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
+    double c = (double)cf, sv = (double)(cf * t0);
+    // exact renormalisation in double: nu = (c^2 + s^2)^(-1/2) = 1 - e/2 + 3e^2/8, e ~ 1e-7 -> error ~ e^3
+    const double e = fma(c, c, fma(sv, sv, -1.0));
+    const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
+    cs[i] = rot ? c * nu : 1.0;                                  // the selects also discard NaNs of degenerate pairs
+    sn[i] = rot ? sv * nu : 0.0;
+    const double tg = rot ? (double)t0 * ga : 0.0;
+    nx[i] = al - tg;
+    ny[i] = be + tg;
+    any |= rot && (g2 > 1e-16 * ab);
+  }
 #pragma unroll
-      for (int k = 0; k < E; ++k) {
-        const double a = x[i][k], b = y[i][k];
-        x[i][k] = cs * a - sn * b;
-        y[i][k] = sn * a + cs * b;
-      }
-      const double tg = (double)t0 * ga;
-      nx[i] = al - tg;
-      ny[i] = be + tg;
-      any |= g2 > 1e-16 * ab;
+  for (int i = 0; i < NR; ++i) {
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const double a = x[i][k], b = y[i][k];
+      x[i][k] = fma(cs[i], a, -sn[i] * b);
+      y[i][k] = fma(sn[i], a, cs[i] * b);
     }
   }
   return any;
@@ -169,16 +196,22 @@ __device__ __forceinline__ bool rotate4(double (&x)[4][E], double (&y)[4][E], do
 template <int NP>
 __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__ partial, int nparts, int n,
                                                       double* __restrict__ Vt, double* __restrict__ lam,
-                                                      int max_sweeps, double tol, int use_chol,
+                                                      int max_sweeps, double tol, int use_chol, int pass_id,
                                                       double* __restrict__ info, double* __restrict__ skip_flag,
-                                                      const double* __restrict__ lam_prev) {
-  // Second-pass protocol: the first pass (use_chol = 1) sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7
-  // (sigma ratio > 3e-4: a single Gram pass is then already accurate to ~1e-12 sigma_max for every singular value);
-  // the second pass (use_chol = 0) sees the flag, returns the identity rotation and the first-pass eigenvalues.
-  if (!use_chol && skip_flag && *skip_flag != 0.0) {
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) lam[e] = lam_prev[e];
-    if (threadIdx.x == 0 && info) info[0] = 0.0;
+                                                      const double* __restrict__ lam_prev, double* __restrict__ Wout,
+                                                      int* __restrict__ flags_out, const int* __restrict__ sub) {
+  if (sub) n = sub[0];                               // sub-block second pass (export mode only)
+  // Second-pass protocol: the first pass sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7 (sigma ratio
+  // > 3e-4: a single Gram pass is then already accurate to ~1e-12 sigma_max for every singular value); the second
+  // pass sees the flag, returns the identity rotation and the first-pass eigenvalues.
+  // Export mode (Wout != nullptr): only the load + Cholesky preconditioning run here; the factor goes to global
+  // memory for the cluster kernel.
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) {
+    if (!Wout) {
+      for (int e = threadIdx.x; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
+      for (int e = threadIdx.x; e < n; e += blockDim.x) lam[e] = lam_prev[e];
+      if (threadIdx.x == 0 && info) info[0] = 0.0;
+    }
     return;
   }
   constexpr int NB = NP / 4;           // row blocks
@@ -268,6 +301,12 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     __syncthreads();
   }
 
+  if (Wout) {                                        // export mode
+    for (int e = tid; e < NP * NP; e += NT) Wout[e] = W[e];
+    for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
+    return;
+  }
+
   const double tol2 = tol * tol;
   int sweeps_done = 0;
   // circle method over the NB blocks: position 0 is fixed, positions 1..NB-1 rotate; warp w plays w against NB-1-w
@@ -313,7 +352,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
           }
           nx[0] = na[p0]; ny[0] = na[q0]; nx[1] = na[p1]; ny[1] = na[q1];
           nx[2] = nb[p0]; ny[2] = nb[q0]; nx[3] = nb[p1]; ny[3] = nb[q1];
-          rotated |= rotate4<E>(x, y, nx, ny, tol2, lane);
+          rotated |= rotateN<4, E>(x, y, nx, ny, tol2, lane);
 #pragma unroll
           for (int k = 0; k < E; ++k) {
             a[p0][k] = x[0][k]; a[q0][k] = y[0][k]; a[p1][k] = x[1][k]; a[q1][k] = y[1][k];
@@ -333,7 +372,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
           for (int k = 0; k < E; ++k) y[i][k] = b[(i + s) & 3][k];
           ny[i] = nb[(i + s) & 3];
         }
-        rotated |= rotate4<E>(a, y, na, ny, tol2, lane);
+        rotated |= rotateN<4, E>(a, y, na, ny, tol2, lane);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -388,7 +427,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     for (int idx = lane; idx < n; idx += 32) Vt[(size_t)rank * n + idx] = W[r * NP + idx] * inv;
     if (lane == 0) lam[rank] = use_chol ? mine : nr;
   }
-  if (use_chol && skip_flag && warp == 0) {
+  if (pass_id == 1 && skip_flag && warp == 0) {
     double mn = 1e300, mx = 0.0;
     for (int r = lane; r < n; r += 32) { mn = fmin(mn, nrm2[r]); mx = fmax(mx, nrm2[r]); }
 #pragma unroll
@@ -400,50 +439,366 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
   }
 }
 
-static cudaError_t jacobi_prepare() {
-  return cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+// ---------------------------------------------------------------------------------------------------
+// Cluster version: the same block-Jacobi ordering with the matrix in global memory (L2-resident) and the block
+// pairs of a block-round spread over the CTAs of ONE thread-block cluster; a cluster barrier (release / acquire at
+// cluster scope, which also orders the global-memory traffic) separates the block-rounds.  Two uses:
+//   n <= 128: 4 CTAs x 4 warps -- every warp has an SM sub-partition to itself instead of sharing it with three
+//             others, which is what bounded the single-CTA kernel (fixed-latency dependency stalls, IPC 0.5);
+//   n <= 512: the matrix no longer fits in one SM's shared memory (bond dimension 128 / 256).
+// E = elements per lane and row (NP = 32 E), K = rows per block.  Rows are read with ld.global.cg (L1 is not
+// coherent across the SMs of a cluster).
+// ---------------------------------------------------------------------------------------------------
+template <int E, int K>
+__global__ void __launch_bounds__(E == 16 ? 256 : 128) k_jacobi_cluster(double* __restrict__ Wg, double* __restrict__ nrm2g,
+                                                        int* __restrict__ flags, int max_sweeps, double tol,
+                                                        double* __restrict__ info, const double* __restrict__ skip_flag,
+                                                        int pass_id, const int* __restrict__ sub) {
+  constexpr int NP = 32 * E, NBmax = NP / K;
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  // active problem size: the whole padded matrix, or (second pass on the small block) the first sub[0] rows
+  int NB = NBmax;
+  if (sub) {
+    const int nact = sub[0];
+    if (nact == 0) return;
+    NB = 2 * ((((nact + K - 1) / K) + 1) / 2);
+    if (NB < 2) NB = 2;
+    if (NB > NBmax) NB = NBmax;
+  }
+  const int TW = NB / 2;                                          // active warps = block pairs per block-round
+  cg::cluster_group cl = cg::this_cluster();
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int gw = (int)cl.block_rank() * wpc + (threadIdx.x >> 5);   // global warp = block pair index
+  const bool active = gw < TW;
+  const double tol2 = tol * tol;
+  int ra = (gw == 0) ? 0 : gw - 1, rb = NB - 2 - gw;
+  int sweeps_done = 0;
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = gw; active && r < NB * K; r += TW) {   // refresh the cached squared row norms
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const double v = __ldcg(Wg + (size_t)r * NP + lane + 32 * k); s = fma(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) nrm2g[r] = s;
+    }
+    cl.sync();
+    bool rotated = false;
+    for (int round = 0; round < NB - 1; ++round) {
+     if (active) {
+      const int bi = (gw == 0) ? 0 : 1 + ra;
+      const int bj = 1 + rb;
+      double a[K][E], b[K][E], na[K], nb[K];
+      double* const wa = Wg + (size_t)K * bi * NP + lane;
+      double* const wb = Wg + (size_t)K * bj * NP + lane;
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          a[i][k] = __ldcg(wa + i * NP + 32 * k);
+          b[i][k] = __ldcg(wb + i * NP + 32 * k);
+        }
+        na[i] = __ldcg(nrm2g + K * bi + i);
+        nb[i] = __ldcg(nrm2g + K * bj + i);
+      }
+      if (round == 0) {   // pairs inside each block, once per sweep
+        if constexpr (K == 4) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int p0 = 0, q0 = s + 1;
+            const int p1 = (s == 0) ? 2 : 1, q1 = (s == 2) ? 2 : 3;
+            double x[4][E], y[4][E], nx[4], ny[4];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+              x[0][k] = a[p0][k]; y[0][k] = a[q0][k]; x[1][k] = a[p1][k]; y[1][k] = a[q1][k];
+              x[2][k] = b[p0][k]; y[2][k] = b[q0][k]; x[3][k] = b[p1][k]; y[3][k] = b[q1][k];
+            }
+            nx[0] = na[p0]; ny[0] = na[q0]; nx[1] = na[p1]; ny[1] = na[q1];
+            nx[2] = nb[p0]; ny[2] = nb[q0]; nx[3] = nb[p1]; ny[3] = nb[q1];
+            rotated |= rotateN<4, E>(x, y, nx, ny, tol2, lane);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+              a[p0][k] = x[0][k]; a[q0][k] = y[0][k]; a[p1][k] = x[1][k]; a[q1][k] = y[1][k];
+              b[p0][k] = x[2][k]; b[q0][k] = y[2][k]; b[p1][k] = x[3][k]; b[q1][k] = y[3][k];
+            }
+            na[p0] = nx[0]; na[q0] = ny[0]; na[p1] = nx[1]; na[q1] = ny[1];
+            nb[p0] = nx[2]; nb[q0] = ny[2]; nb[p1] = nx[3]; nb[q1] = ny[3];
+          }
+        } else {
+          double x[2][E], y[2][E], nx[2], ny[2];
+#pragma unroll
+          for (int k = 0; k < E; ++k) { x[0][k] = a[0][k]; y[0][k] = a[1][k]; x[1][k] = b[0][k]; y[1][k] = b[1][k]; }
+          nx[0] = na[0]; ny[0] = na[1]; nx[1] = nb[0]; ny[1] = nb[1];
+          rotated |= rotateN<2, E>(x, y, nx, ny, tol2, lane);
+#pragma unroll
+          for (int k = 0; k < E; ++k) { a[0][k] = x[0][k]; a[1][k] = y[0][k]; b[0][k] = x[1][k]; b[1][k] = y[1][k]; }
+          na[0] = nx[0]; na[1] = ny[0]; nb[0] = nx[1]; nb[1] = ny[1];
+        }
+      }
+      // the K*K pairs across the two blocks: set s pairs a[i] with b[(i+s) % K]
+#pragma unroll
+      for (int s = 0; s < K; ++s) {
+        double y[K][E], ny[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) y[i][k] = b[(i + s) % K][k];
+          ny[i] = nb[(i + s) % K];
+        }
+        rotated |= rotateN<K, E>(a, y, na, ny, tol2, lane);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) b[(i + s) % K][k] = y[i][k];
+          nb[(i + s) % K] = ny[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          wa[i * NP + 32 * k] = a[i][k];
+          wb[i * NP + 32 * k] = b[i][k];
+        }
+        if (lane == 0) { nrm2g[K * bi + i] = na[i]; nrm2g[K * bj + i] = nb[i]; }
+      }
+      ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+      rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+     }
+      cl.sync();
+    }
+    if (rotated && lane == 0) atomicExch(flags + sweep, 1);
+    sweeps_done = sweep + 1;
+    cl.sync();
+    const int any = __ldcg(flags + sweep);
+    if (!any) break;
+  }
+  if (gw == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
 }
 
-static void launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
-                          double* info, double* skip, const double* lam_prev, cudaStream_t st) {
-  TNML_COUNT(1);
-  if (n > 64)
-    k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
-  else if (n > 32)
-    k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
-  else
-    k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, info, skip, lam_prev);
+// Ranking + normalisation after the cluster sweeps (one CTA): squared row norms rank the rows (descending, ties
+// by index); Vt[k] = k-th unit row, lam[k] = eigenvalue of the Gram matrix; sets the second-pass skip flag.
+__global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict__ Wg, int NP, int n, int use_chol,
+                                                       int pass_id, double* __restrict__ Vt, double* __restrict__ lam,
+                                                       double* __restrict__ skip_flag, const double* __restrict__ lam_prev,
+                                                       double* __restrict__ info, int* __restrict__ sub) {
+  __shared__ double nrm[SVD_MAXN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) {
+    for (int e = tid; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
+    for (int e = tid; e < n; e += blockDim.x) lam[e] = lam_prev[e];
+    if (tid == 0 && info) info[0] = 0.0;
+    return;
+  }
+  // Second pass on the small block: the decomposition of the ns x ns block goes to the lower-right corner of an
+  // otherwise identity rotation; the first k0 eigenvalues are the first pass's.
+  const int nfull = n;
+  int k0 = 0;
+  if (pass_id == 2 && sub) {
+    n = sub[0];
+    k0 = sub[1];
+    for (int e = tid; e < nfull * nfull; e += blockDim.x) {
+      const int r = e / nfull, c = e % nfull;
+      if (r < k0 || c < k0) Vt[e] = (r == c) ? 1.0 : 0.0;
+    }
+    for (int e = tid; e < k0; e += blockDim.x) lam[e] = lam_prev[e];
+  }
+  for (int r = warp; r < n; r += NW) {
+    double s = 0.0;
+    for (int idx = lane; idx < n; idx += 32) { double v = Wg[(size_t)r * NP + idx]; s = fma(v, v, s); }
+    s = warp_sum(s);
+    if (lane == 0) nrm[r] = s;
+  }
+  __syncthreads();
+  for (int r = warp; r < n; r += NW) {
+    const double mine = nrm[r];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) {
+      double other = nrm[o];
+      rank += (other > mine) || (other == mine && o < r);
+    }
+    const double nr = sqrt(mine);
+    const double inv = mine > 0.0 ? 1.0 / nr : 0.0;
+    for (int idx = lane; idx < n; idx += 32)
+      Vt[(size_t)(k0 + rank) * nfull + k0 + idx] = Wg[(size_t)r * NP + idx] * inv;
+    if (lane == 0) lam[k0 + rank] = use_chol ? mine : nr;
+  }
+  if (pass_id == 1 && skip_flag && warp == 0) {
+    // Which singular values does a single Gram pass leave inaccurate (error ~ eps sigma_max^2 / sigma)?  Those below
+    // 1e-3 sigma_max: they form the trailing block (the rows are sorted), refined by the second pass; none -> skip.
+    double mx = 0.0;
+    for (int r = lane; r < n; r += 32) mx = fmax(mx, nrm[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // squared row norms are sigma^2 (Cholesky factor) or sigma^4 (plain Gram matrix)
+    const double thr = (use_chol ? 1e-6 : 1e-12) * mx;
+    int cnt = 0;
+    for (int r = lane; r < n; r += 32) cnt += nrm[r] < thr;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+      *skip_flag = (cnt == 0) ? 1.0 : 0.0;
+      if (sub) { sub[0] = cnt; sub[1] = n - cnt; }
+    }
+  }
+}
+
+// Wg (NP x NP, zero padded; NP == n gives the plain n x n matrix) = sum of the Gram partials in a fixed order;
+// also clears the sweep flags.  Many CTAs: one CTA summing 40 partials took 86 us.
+__global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__ partial, int nparts, int n, int NP,
+                                                      double* __restrict__ Wg, int* __restrict__ flags,
+                                                      const double* __restrict__ skip_flag, int pass_id,
+                                                      const int* __restrict__ sub, int unpadded) {
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;
+  if (sub) {
+    n = sub[0];
+    if (unpadded) NP = n;
+    if (n == 0) return;
+  }
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < 64) flags[e] = 0;
+  if (e >= NP * NP) return;
+  const int r = e / NP, c = e % NP;
+  double s = 0.0;
+  if (r < n && c < n)
+    for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * n * n + (size_t)r * n + c];
+  Wg[e] = s;
+}
+
+static int jacobi_cluster_enabled() {   // TNML_JACOBI_CLUSTER=0 keeps n <= 128 on the single-CTA kernel (A/B knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_JACOBI_CLUSTER");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
+template <int E, int K>
+__global__ void k_jacobi_cluster(double*, double*, int*, int, double, double*, const double*, int, const int*);
+
+static cudaError_t jacobi_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+  if (e != cudaSuccess) return e;
+  // n = 512 uses a cluster of 16 CTAs (above the portable limit of 8)
+  return cudaFuncSetAttribute(k_jacobi_cluster<16, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+}
+
+template <int E, int K>
+static cudaError_t launch_cluster(int ctas, int threads, double* Wg, double* nrm2g, int* flags, double tol,
+                                  double* info, const double* skip, int pass_id, const int* sub, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_sweeps = 60;
+  return cudaLaunchKernelEx(&cfg, k_jacobi_cluster<E, K>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub);
+}
+
+struct JacobiBuffers {
+  double *Wg, *nrm2g;
+  int* flags;
+  double* scratch;   // n x n, free while the first-pass eigen-decomposition runs (the Y buffer)
+};
+
+// Eigen-decomposition of the Gram matrix given by its partial sums.  use_chol only applies to n <= 128.
+// sub (device {ns, k0}) : written by the first pass; when passed to the second pass, only the trailing ns x ns block
+// (the small singular values) is decomposed -- the partials then hold that block's Gram matrix.
+static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
+                         int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
+                         cudaStream_t st) {
+  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+  if (!cluster) {
+    TNML_COUNT(1);
+    if (n > 64)
+      k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
+                                                   lam_prev, nullptr, nullptr, nullptr);
+    else if (n > 32)
+      k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
+                                                lam_prev, nullptr, nullptr, nullptr);
+    else
+      k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
+                                                lam_prev, nullptr, nullptr, nullptr);
+    return tnml_launch_status();
+  }
+  const int* sub2 = (pass_id == 2) ? sub : nullptr;   // sub-block mode of the second pass
+  cudaError_t e;
+  int NP;
+  TNML_COUNT(3);
+  if (n <= 128) {
+    NP = 128;
+    if (use_chol) {
+      // sum the partials (many CTAs) into scratch, Cholesky-precondition in one CTA (export mode), then 4 CTAs x 4 warps
+      double* scratch = (pass_id == 1) ? jb.scratch : Vt;   // Vt is only written by the finish kernel at the very end
+      TNML_COUNT(1);
+      k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, nparts, n, n, scratch, jb.flags, skip, pass_id, sub2,
+                                                            1);
+      k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(scratch, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info, skip,
+                                                   lam_prev, jb.Wg, jb.flags, sub2);
+    } else {
+      k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id,
+                                                              sub2, 0);
+    }
+    e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+  } else {
+    use_chol = 0;
+    NP = n <= 256 ? 256 : 512;
+    k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id, sub2,
+                                                            0);
+    if (NP == 256) e = launch_cluster<8, 4>(8, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    else e = launch_cluster<16, 2>(16, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+  }
+  if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+  k_jacobi_finish<<<1, 512, 0, st>>>(jb.Wg, NP, n, use_chol, pass_id, Vt, lam, skip, lam_prev, info, sub);
+  return tnml_launch_status();
 }
 
 // Out[k][l] = scale_k * sum_s Vt[k][s] In(s,l), k < kmax; scale_k = lam_k^(-1/4) if lam != nullptr else 1
-// written at out + k*kstride + map(l).  grid = (ceil(Nl/32), ceil(kmax/32)), 256 threads.
+// written at out + k*kstride + map(l).  grid = (ceil(Nl/32), ceil(kmax/32)), 256 threads; s in chunks of 128.
+constexpr int ROWS_SC = 64;
 __global__ void __launch_bounds__(256) k_rows(const double* __restrict__ X, long long ss, long long sl, int n, int Nl,
                                               const double* __restrict__ Vt, const double* __restrict__ lam, int kmax,
                                               double* __restrict__ out, long long kstride, Idx3 map) {
-  extern __shared__ __align__(16) double sm[];
-  double* Vs = sm;                 // [32][n+1]
-  double* Is = sm + 32 * (n + 1);  // [n][33]
+  __shared__ double Vs[32][ROWS_SC + 1];
+  __shared__ double Is[ROWS_SC][33];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-  for (int e = tid; e < 32 * n; e += 256) {
-    int k = e / n, s = e % n;
-    Vs[k * (n + 1) + s] = (k0 + k < kmax) ? Vt[(size_t)(k0 + k) * n + s] : 0.0;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int s0 = 0; s0 < n; s0 += ROWS_SC) {
+    const int sn = min(ROWS_SC, n - s0);
+    __syncthreads();
+    for (int e = tid; e < 32 * ROWS_SC; e += 256) {
+      const int k = e / ROWS_SC, s = e % ROWS_SC;
+      Vs[k][s] = (k0 + k < kmax && s < sn) ? Vt[(size_t)(k0 + k) * n + s0 + s] : 0.0;
+    }
+    for (int e = tid; e < 32 * ROWS_SC; e += 256) {
+      int s, lj;
+      if (sl == 1) { lj = e & 31; s = e >> 5; } else { s = e % ROWS_SC; lj = e / ROWS_SC; }
+      Is[s][lj] = (l0 + lj < Nl && s < sn) ? X[(long long)(s0 + s) * ss + (long long)(l0 + lj) * sl] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = warp + 8 * i;
+      double s = acc[i];
+      for (int t = 0; t < sn; ++t) s = fma(Vs[k][t], Is[t][lane], s);
+      acc[i] = s;
+    }
   }
-  for (int e = tid; e < 32 * n; e += 256) {
-    int s, lj;
-    if (sl == 1) { lj = e & 31; s = e >> 5; } else { s = e % n; lj = e / n; }
-    Is[s * 33 + lj] = (l0 + lj < Nl) ? X[(long long)s * ss + (long long)(l0 + lj) * sl] : 0.0;
-  }
-  __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = warp + 8 * i;
-    double s = 0.0;
-    for (int t = 0; t < n; ++t) s = fma(Vs[k * (n + 1) + t], Is[t * 33 + lane], s);
     if (k0 + k < kmax && l0 + lane < Nl) {
       double sc = 1.0;
       if (lam) { double lv = lam[k0 + k]; sc = lv > 0.0 ? 1.0 / sqrt(sqrt(lv)) : 0.0; }
-      out[(long long)(k0 + k) * kstride + map(l0 + lane)] = sc * s;
+      out[(long long)(k0 + k) * kstride + map(l0 + lane)] = sc * acc[i];
     }
   }
 }
@@ -468,12 +823,39 @@ __global__ void __launch_bounds__(256) k_short(const double* __restrict__ Vt1, c
 }
 
 struct SvdPlan {
-  int R, C, n, Nl, nparts;
+  int R, C, n, Nl, nparts, lc, NP;
   bool rows_short;
-  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, total;
+  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, off_Wg, off_nrm, off_flags, off_sub, total;
 };
 
-static SvdPlan svd_plan_rc(int R, int C);
+static SvdPlan svd_plan_rc(int R, int C) {
+  SvdPlan p;
+  p.R = R;
+  p.C = C;
+  p.rows_short = p.R <= p.C;
+  p.n = p.rows_short ? p.R : p.C;
+  p.Nl = p.rows_short ? p.C : p.R;
+  // long-side chunk per Gram CTA: 32 columns for the usual sizes, wider for huge matrices (bounded partial buffer)
+  p.lc = 32;
+  while (tnml_cdiv(p.Nl, p.lc) > 64) p.lc *= 2;
+  p.nparts = tnml_cdiv(p.Nl, p.lc);
+  p.NP = p.n <= 128 ? 128 : (p.n <= 256 ? 256 : 512);
+  size_t o = 0;
+  p.off_partial = o; o += (size_t)p.nparts * p.n * p.n;
+  p.off_vt1 = o; o += (size_t)p.n * p.n;
+  p.off_vt2 = o; o += (size_t)p.n * p.n;
+  p.off_lam1 = o; o += p.n;
+  p.off_lam2 = o; o += p.n;
+  p.off_Y = o; o += (size_t)p.n * p.Nl;
+  p.off_skip = o; o += 1;
+  p.off_Wg = o; o += (size_t)p.NP * p.NP;
+  p.off_nrm = o; o += p.NP;
+  p.off_flags = o; o += 32;   // 64 ints
+  p.off_sub = o; o += 1;      // 2 ints
+  p.total = o;
+  return p;
+}
+
 static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
   return svd_plan_rc(left_dir ? 2 * Dl * L : 2 * Dl, left_dir ? 2 * Dr : 2 * L * Dr);
 }
@@ -486,60 +868,48 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   if (!attr_set) {
     cudaError_t e = jacobi_prepare();
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    e = cudaFuncSetAttribute(k_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * (SVD_MAXN + 1) + SVD_MAXN * 33) * 8);
-    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     attr_set = true;
   }
   double *partial = w + p.off_partial, *vt1 = w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
          *lam2 = w + p.off_lam2, *Y = w + p.off_Y, *skip = w + p.off_skip;
+  JacobiBuffers jb{w + p.off_Wg, w + p.off_nrm, (int*)(w + p.off_flags), Y};
   const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
   const int n = p.n, Nl = p.Nl;
   const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
-  const size_t rsmem = (size_t)(32 * (n + 1) + n * 33) * 8;
   double* dst_short = p.rows_short ? dst_rows : dst_cols;
   double* dst_long = p.rows_short ? dst_cols : dst_rows;
   const Idx3 map_short = p.rows_short ? rowmap : colmap, map_long = p.rows_short ? colmap : rowmap;
   const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
+  const int tiles = tnml_cdiv(n, GRAM_TILE);
+  const dim3 ggrid(p.nparts, tiles, tiles);
+  double* skip1 = refine == 1 ? skip : nullptr;
+  // refine == 1 on the cluster path: the second pass only decomposes the block of small singular values
+  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+  int* sub = (refine == 1 && cluster) ? (int*)(w + p.off_sub) : nullptr;
+  int rc;
 
   TNML_COUNT(1);
-  k_gram<<<p.nparts, 256, 0, st>>>(X, ss, sl, n, Nl, partial, nullptr);
-  launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, svals + n, refine == 1 ? skip : nullptr, nullptr, st);
+  k_gram<<<ggrid, 256, 0, st>>>(X, ss, sl, n, Nl, p.lc, partial, nullptr, nullptr);
+  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st);
+  if (rc) return rc;
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
     TNML_COUNT(4);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
-    k_gram<<<p.nparts, 256, 0, st>>>(Y, Nl, 1, n, Nl, partial, refine == 1 ? skip : nullptr);
-    launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 0, svals + n + 1, refine == 1 ? skip : nullptr, lam1, st);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
-                                                                        k_long_stride, map_long);
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
+    k_gram<<<ggrid, 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip1, sub);
+    rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, sub ? 1 : 0, 2, svals + n + 1, skip1, lam1, jb, sub,
+                       st);
+    if (rc) return rc;
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, 0, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
+                                                                    k_long_stride, map_long);
     k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short, svals);
   } else {
     TNML_COUNT(2);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, rsmem, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
-                                                                        k_long_stride, map_long);
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
+                                                                    k_long_stride, map_long);
     k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short, svals);
   }
   return tnml_launch_status();
-}
-
-static SvdPlan svd_plan_rc(int R, int C) {
-  SvdPlan p;
-  p.R = R;
-  p.C = C;
-  p.rows_short = p.R <= p.C;
-  p.n = p.rows_short ? p.R : p.C;
-  p.Nl = p.rows_short ? p.C : p.R;
-  p.nparts = tnml_cdiv(p.Nl, GRAM_LC);
-  size_t o = 0;
-  p.off_partial = o; o += (size_t)p.nparts * p.n * p.n;
-  p.off_vt1 = o; o += (size_t)p.n * p.n;
-  p.off_vt2 = o; o += (size_t)p.n * p.n;
-  p.off_lam1 = o; o += p.n;
-  p.off_lam2 = o; o += p.n;
-  p.off_Y = o; o += (size_t)p.n * p.Nl;
-  p.off_skip = o; o += 1;
-  p.total = o;
-  return p;
 }
 
 }  // namespace tnml

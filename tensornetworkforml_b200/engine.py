@@ -104,6 +104,7 @@ class SweepEngine:
         self.y_dev = None
         self.hist = None
         self._pinned = None
+        self._registered = []         # host buffers page-locked in place: [(ptr, nbytes)]
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
@@ -113,6 +114,25 @@ class SweepEngine:
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _host_register(self, arr):
+        """cudaHostRegister the NumPy buffer once (keeps the last two distinct buffers registered)."""
+        ptr, nbytes = arr.ctypes.data, arr.nbytes
+        key = (ptr, nbytes)
+        if key in self._registered:
+            return True
+        rt = torch.cuda.cudart()
+        while len(self._registered) >= 2:
+            old_ptr, _ = self._registered.pop(0)
+            rt.cudaHostUnregister(old_ptr)
+        try:
+            err = rt.cudaHostRegister(ptr, nbytes, 0)
+        except Exception:
+            return False
+        if int(err) != 0:
+            return False
+        self._registered.append(key)
+        return True
 
     def _side_stream(self):
         if self._side is None:
@@ -200,15 +220,20 @@ class SweepEngine:
             Xd = X.to(torch.float64).contiguous()
             Ns = Xd.shape[0]
         else:
-            X = np.asarray(X)
+            X = np.ascontiguousarray(X, dtype=np.float64)
             Ns = X.shape[0]
-            Xh = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
-            if self._pinned is None or self._pinned.numel() < Xh.numel():
-                self._pinned = torch.empty(Xh.numel(), dtype=torch.float64).pin_memory()
-            pin = self._pinned[:Xh.numel()]
-            pin.copy_(Xh.reshape(-1))
+            Xh = torch.from_numpy(X).reshape(-1)
             Xd = self._workspace("xstage", Xh.numel() * 8)[:Xh.numel()]
-            Xd.copy_(pin, non_blocking=True)
+            if Xh.numel() * 8 >= (8 << 20) and self._host_register(X):
+                # the caller's buffer is page-locked in place (cached by address): the DMA engine reads it directly,
+                # no pageable -> pinned staging copy (which cost ~100 ms for the 188 MB batch of config 3)
+                Xd.copy_(Xh, non_blocking=True)
+            else:
+                if self._pinned is None or self._pinned.numel() < Xh.numel():
+                    self._pinned = torch.empty(Xh.numel(), dtype=torch.float64).pin_memory()
+                pin = self._pinned[:Xh.numel()]
+                pin.copy_(Xh)
+                Xd.copy_(pin, non_blocking=True)
         assert Xd.numel() == Ns * self.S * 2, "input must have shape (Ns, S, 2)"
         self._alloc_batch(Ns)
         call("tnml_pack_features", _ptr(Xd), _ptr(self.phi), Ns, self.S, F64, self._stream())

@@ -259,13 +259,17 @@ def _run_svd(L, B, left_dir, m, refine=2):
 @pytest.mark.parametrize("refine", [2, 1, 0])
 @pytest.mark.parametrize("Dl,Dr,nl,left_dir,m", [(4, 4, 3, 0, 4), (4, 4, 3, 1, 4), (64, 64, 10, 0, 64),
                                                  (64, 64, 10, 1, 64), (1, 5, 2, 0, 2), (5, 1, 2, 1, 2), (4, 1, 2, 0, 4),
-                                                 (1, 3, 2, 1, 4), (2, 2, 2, 0, 2), (7, 5, 3, 0, 9), (3, 9, 2, 1, 5)])
+                                                 (1, 3, 2, 1, 4), (2, 2, 2, 0, 2), (7, 5, 3, 0, 9), (3, 9, 2, 1, 5),
+                                                 (128, 128, 3, 0, 128), (100, 90, 2, 1, 77), (256, 256, 2, 0, 256),
+                                                 (200, 256, 2, 1, 130)])
 def test_svd_split(L, Dl, Dr, nl, left_dir, m, refine):
     rng = np.random.default_rng(10)
     B = rng.standard_normal((Dl, 2, nl, 2, Dr))
     Mx = B.reshape(Dl * 2, -1) if not left_dir else B.reshape(Dl * 2 * nl, 2 * Dr)
     U, S, Vh = np.linalg.svd(Mx, full_matrices=False)
     m = min(m, len(S))
+    if max(Dl, Dr) > 64 and refine != 2:
+        pytest.skip("large sizes are exercised with the full two-pass variant only")
     sv, prod, Ap, Aq = _run_svd(L, B, left_dir, m, refine)
     assert np.abs(sv - S).max() / S.max() < 1e-12
     want = ((U[:, :m] * S[:m]) @ Vh[:m]).reshape(B.shape)
@@ -288,6 +292,27 @@ def test_svd_small_singular_values_need_the_second_pass(L):
     assert np.abs(sv - S).max() < 1e-13
     sv0, _, _, _ = _run_svd(L, B, 0, R, refine=0)
     assert np.abs(sv0 - S).max() < 1e-6          # single Gram pass: sqrt(eps)-level only
+
+
+@pytest.mark.parametrize("Dl,Dr,nl,left_dir", [(40, 40, 2, 0), (64, 64, 3, 0), (30, 50, 2, 1), (100, 100, 2, 0)])
+def test_svd_two_scale_spectrum_small_block_refinement(L, Dl, Dr, nl, left_dir):
+    """The spectrum of a trained bond tensor: half the singular values O(1), the other half 1e-5 .. 1e-10 (what is
+    discarded).  refine=1 decomposes only the small block in its second pass; every singular value must still be
+    accurate to ~eps * sigma_max, and the kept part of the split exact."""
+    rng = np.random.default_rng(15)
+    R, C = (2 * Dl, 2 * nl * Dr) if not left_dir else (2 * Dl * nl, 2 * Dr)
+    n = min(R, C)
+    Q1, _ = np.linalg.qr(rng.standard_normal((R, n)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((C, n)))
+    S = np.concatenate([np.logspace(0, -1, n // 2), np.logspace(-5, -10, n - n // 2)])
+    Mx = (Q1 * S) @ Q2.T
+    B = Mx.reshape(Dl, 2, nl, 2, Dr)
+    m = n // 2
+    for refine in (1, 2):
+        sv, prod, _, _ = _run_svd(L, B, left_dir, m, refine)
+        assert np.abs(sv - S).max() < 2e-13, "refine=%d" % refine
+        want = ((Q1[:, :m] * S[:m]) @ Q2[:, :m].T).reshape(B.shape)
+        assert np.abs(prod - want).max() < 1e-11
 
 
 def test_svd_rank_deficient(L):

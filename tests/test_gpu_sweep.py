@@ -74,12 +74,13 @@ def test_known_answer_trained_diag_model(tn):
     ("linear", "MSE", True, 0.01, "fixed", 10, 16),
     ("softmax", "full_cross_ent", False, 1e-3, "fixed", 4, 8),
     ("sigmoid", "MSE", True, 0.1, "fixed", 3, 12),
+    ("linear", "MSE", True, 0.01, "fixed", 3, 96),      # bond dimension > 64: chunked GEMMs, cluster Jacobi (n = 192)
 ])
 def test_seeded_constructor_and_sweeps_match_oracle(tn, act, loss, L2, wd, rule, Lbl, D):
     """Public constructor with the reference's RNG order + calibration, then sweeps vs the oracle: sweeps 1-2 run
     free, later sweeps are re-synchronised to the oracle's state first (the iteration is
     chaotic -- a 1e-15 perturbation grows to ~1e-11 after three reference sweeps)."""
-    S, Ns, lr = 12, 300, 0.02
+    S, Ns, lr = (12, 300, 0.02) if D <= 16 else (16, 160, 0.02)
     np.random.seed(21)
     X = O.feature_map(np.random.random((Ns, S)))
     y = np.random.randint(0, Lbl, Ns)
