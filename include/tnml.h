@@ -103,8 +103,10 @@ int tnml_grad(const void* q, const void* Lenv, const void* Renv, void* dB, void*
 int tnml_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, double alpha, const void* A, int32_t lda,
               const void* B, int32_t ldb, double beta, void* C, int32_t ldc, int32_t dtype, tnml_stream_t stream);
 int64_t tnml_project_workspace_bytes(int64_t Ns, int32_t Dl, int32_t Dr, int32_t L);
+/* max_ctas: 0 = fill all SMs; otherwise cap the grid (the caller runs the SVD split beside the projection and
+ * leaves whole GPCs free for its thread-block clusters). */
 int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Renv, void* f, void* ws, int64_t Ns,
-                 int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream);
+                 int32_t Dl, int32_t Dr, int32_t L, int32_t max_ctas, int32_t dtype, tnml_stream_t stream);
 
 /* ---- a10/a14: regularisation, clipping, update --------------------------------------------------------
  * tnml_l2_term     : G = E_L . B . E_R (the derivative of the squared norm w.r.t. B)        NC:1129-1135

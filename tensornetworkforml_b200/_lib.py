@@ -33,7 +33,7 @@ SIGNATURES = {
     "tnml_grad": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "tnml_gemm": (C.c_int, [_i32, _i32, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _i32, _f64, _vp, _i32, _i32, _vp]),
     "tnml_project_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
-    "tnml_project": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_project": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_bond_update_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "tnml_l2_term": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tnml_bond_update": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _i32, _i32, _vp]),

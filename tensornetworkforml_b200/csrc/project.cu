@@ -5,6 +5,8 @@
 //   f[b][l]      += sum_{st,c} pp[b][st] * R[b][c] * T[b][(st, c)]                                 -> epilogue
 // The B' slice (64 x 256) stays resident in shared memory for the whole CTA (weight-stationary); samples are
 // streamed in 32-row stages through a cp.async pipeline.  grid = (L * c_chunks, ksplit).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tnml {
@@ -155,10 +157,11 @@ __global__ void __launch_bounds__(256) k_fpart_reduce(const double* __restrict__
   f[e] = s;
 }
 
-static void project_plan(int64_t Ns, int Dr, int L, int* cols, int* ks, int64_t* chunk) {
+static void project_plan(int64_t Ns, int Dr, int L, int max_ctas, int* cols, int* ks, int64_t* chunk) {
   int c_chunks = tnml_cdiv(Dr, 64);
   *cols = L * c_chunks;
-  int k = kNumSMs / *cols;
+  const int budget = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+  int k = budget / *cols;
   int kmax = tnml_cdiv(Ns, 2 * PJ_BM);
   if (k > kmax) k = kmax;
   if (k < 1) k = 1;
@@ -178,7 +181,8 @@ extern "C" int64_t tnml_project_workspace_bytes(int64_t Ns, int32_t Dl, int32_t 
 }
 
 extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Renv, void* f, void* ws,
-                            int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream) {
+                            int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t max_ctas, int32_t dtype,
+                            tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(B && pp && Lenv && Renv && f && ws && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
   static bool attr_set = false;
@@ -191,7 +195,7 @@ extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, con
   }
   int cols, ks;
   int64_t chunk;
-  project_plan(Ns, Dr, L, &cols, &ks, &chunk);
+  project_plan(Ns, Dr, L, max_ctas, &cols, &ks, &chunk);
   const int c_chunks = tnml_cdiv(Dr, 64), a_chunks = tnml_cdiv(Dl, 64);
   dim3 grid(cols, ks);
   // the left bond is contracted 64 rows at a time; successive launches accumulate (deterministic: stream order)

@@ -269,13 +269,22 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     for (int k = 0; k < n; ++k) {
       const int c = piv_idx;
       if (c < 0) break;                                  // numerically rank deficient from here on
-      double acc = 0.0;                                  // this group's share of sum_m R_m[c] R_m[j]
-#pragma unroll 4
-      for (int m = gq; m < k; m += NG) {
-        const int rm = piv[m];
-        acc = fma(W[rm * NP + c], W[rm * NP + j], acc);
+      // this group's share of sum_m R_m[c] R_m[j]; four accumulators: the FP64 FMA latency (~36 cycles) is what
+      // bounds this loop, not its throughput
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      int m = gq;
+      for (; m + 3 * NG < k; m += 4 * NG) {
+        const int r0 = piv[m], r1 = piv[m + NG], r2 = piv[m + 2 * NG], r3 = piv[m + 3 * NG];
+        acc0 = fma(W[r0 * NP + c], W[r0 * NP + j], acc0);
+        acc1 = fma(W[r1 * NP + c], W[r1 * NP + j], acc1);
+        acc2 = fma(W[r2 * NP + c], W[r2 * NP + j], acc2);
+        acc3 = fma(W[r3 * NP + c], W[r3 * NP + j], acc3);
       }
-      part[gq][j] = acc;
+      for (; m < k; m += NG) {
+        const int rm = piv[m];
+        acc0 = fma(W[rm * NP + c], W[rm * NP + j], acc0);
+      }
+      part[gq][j] = (acc0 + acc1) + (acc2 + acc3);
       __syncthreads();
       if (gq == 0) {
         double scc = W[c * NP + c], sj = W[c * NP + j];
@@ -576,6 +585,152 @@ __global__ void __launch_bounds__(E == 16 ? 256 : 128) k_jacobi_cluster(double* 
   if (gw == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster version 2: ONE WARP PER ROTATION.  Same block ordering (blocks of 4 rows, round-robin over block pairs,
+// cluster barrier between block-rounds), but the 8 rows of a block pair are staged in shared memory and its
+// 4 + 4 + ... rotation sets are executed by FOUR warps, one rotation each, separated by a named barrier of those
+// 128 threads.  The sequential chain per sweep (n - 1 rotation sets) then costs one rotation's latency per set
+// instead of four interleaved ones in a single instruction stream (ncu: IPC 0.2 per warp, fixed-latency stalls).
+// E = elements per lane and row (NP = 32 E).  blockDim = 128 * (block pairs per CTA).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+template <int E>
+__device__ __forceinline__ bool rotate_pair(double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ nx,
+                                            double* __restrict__ ny, double tol2, int lane) {
+  double x[E], y[E];
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    x[k] = rx[lane + 32 * k];
+    y[k] = ry[lane + 32 * k];
+    if (k & 1) a1 = fma(x[k], y[k], a1);
+    else a0 = fma(x[k], y[k], a0);
+  }
+  const double al = *nx, be = *ny;
+  const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
+  const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
+  const float df = (float)((be - al) * sc);
+  const double thr = tol2 * al * be, big = 1e-16 * al * be;
+  const double ga = warp_sum(a0 + a1);
+  const double g2 = ga * ga;
+  if (!(g2 > thr) || ex == 0 || ex >= 2040) return false;
+  const float tf = (float)((ga + ga) * sc);
+  const float hh = fmaf(df, df, tf * tf);
+  const float h = hh * rsqrt_approx(hh);
+  const float t0 = __fdividef(tf, df + copysignf(h, df));
+  const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
+  double cs = (double)cf, sn = (double)(cf * t0);
+  const double e = fma(cs, cs, fma(sn, sn, -1.0));
+  const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
+  cs *= nu;
+  sn *= nu;
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    rx[lane + 32 * k] = fma(cs, x[k], -sn * y[k]);
+    ry[lane + 32 * k] = fma(sn, x[k], cs * y[k]);
+  }
+  if (lane == 0) {
+    const double tg = (double)t0 * ga;
+    *nx = al - tg;
+    *ny = be + tg;
+  }
+  return g2 > big;
+}
+
+template <int E>
+__global__ void __launch_bounds__(512) k_jacobi_cluster_w(double* __restrict__ Wg, double* __restrict__ nrm2g,
+                                                          int* __restrict__ flags, int max_sweeps, double tol,
+                                                          double* __restrict__ info, const double* __restrict__ skip_flag,
+                                                          int pass_id, const int* __restrict__ sub) {
+  constexpr int NP = 32 * E, K = 4, NBmax = NP / K;
+  extern __shared__ __align__(16) double sm[];   // per block pair: 8 rows x NP, then 8 norms
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  int NB = NBmax;
+  if (sub) {
+    const int nact = sub[0];
+    if (nact == 0) return;
+    NB = 2 * ((((nact + K - 1) / K) + 1) / 2);
+    if (NB < 2) NB = 2;
+    if (NB > NBmax) NB = NBmax;
+  }
+  const int TW = NB / 2;                                          // active block pairs per block-round
+  cg::cluster_group cl = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bpl = warp >> 2, w = warp & 3;                        // local block pair, role inside the pair
+  const int bpc = blockDim.x >> 7;                                // block pairs per CTA
+  const int bp = (int)cl.block_rank() * bpc + bpl;                // global block pair index
+  const int gwarp = (int)cl.block_rank() * (blockDim.x >> 5) + warp, nwarps = (int)cl.num_blocks() * (blockDim.x >> 5);
+  const bool active = bp < TW;
+  double* rows = sm + (size_t)bpl * (8 * NP + 8);
+  double* nr = rows + 8 * NP;
+  const double tol2 = tol * tol;
+  int ra = (bp == 0) ? 0 : bp - 1, rb = NB - 2 - bp;
+  int sweeps_done = 0;
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = gwarp; r < NB * K; r += nwarps) {   // refresh the cached squared row norms
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const double v = __ldcg(Wg + (size_t)r * NP + lane + 32 * k); s = fma(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) nrm2g[r] = s;
+    }
+    cl.sync();
+    bool rotated = false;
+    for (int round = 0; round < NB - 1; ++round) {
+      if (active) {
+        const int bi = (bp == 0) ? 0 : 1 + ra;
+        const int bj = 1 + rb;
+        // stage: warp w brings row w of each block (rows 0-3 = block bi, 4-7 = block bj)
+        double* const ga_ = Wg + (size_t)(K * bi + w) * NP + lane;
+        double* const gb_ = Wg + (size_t)(K * bj + w) * NP + lane;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          rows[w * NP + lane + 32 * k] = __ldcg(ga_ + 32 * k);
+          rows[(4 + w) * NP + lane + 32 * k] = __ldcg(gb_ + 32 * k);
+        }
+        if (lane == 0) { nr[w] = __ldcg(nrm2g + K * bi + w); nr[4 + w] = __ldcg(nrm2g + K * bj + w); }
+        pair_barrier(1 + bpl);
+        if (round == 0) {   // pairs inside each block, once per sweep: (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2), both blocks
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int base = (w >> 1) * 4, j = w & 1;
+            int p, q;
+            if (s == 0) { p = 2 * j; q = 2 * j + 1; }
+            else if (s == 1) { p = j; q = j + 2; }
+            else { p = j; q = 3 - j; }
+            rotated |= rotate_pair<E>(rows + (base + p) * NP, rows + (base + q) * NP, nr + base + p, nr + base + q, tol2,
+                                      lane);
+            pair_barrier(1 + bpl);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {   // the 16 pairs across the two blocks: warp w rotates (w, 4 + (w+s)%4)
+          const int q = 4 + ((w + s) & 3);
+          rotated |= rotate_pair<E>(rows + w * NP, rows + q * NP, nr + w, nr + q, tol2, lane);
+          pair_barrier(1 + bpl);
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          ga_[32 * k] = rows[w * NP + lane + 32 * k];
+          gb_[32 * k] = rows[(4 + w) * NP + lane + 32 * k];
+        }
+        if (lane == 0) { nrm2g[K * bi + w] = nr[w]; nrm2g[K * bj + w] = nr[4 + w]; }
+        ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+        rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+      }
+      cl.sync();
+    }
+    if (rotated && lane == 0) atomicExch(flags + sweep, 1);
+    sweeps_done = sweep + 1;
+    cl.sync();
+    const int any = __ldcg(flags + sweep);
+    if (!any) break;
+  }
+  if (gwarp == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
+}
+
 // Ranking + normalisation after the cluster sweeps (one CTA): squared row norms rank the rows (descending, ties
 // by index); Vt[k] = k-th unit row, lam[k] = eigenvalue of the Gram matrix; sets the second-pass skip flag.
 __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict__ Wg, int NP, int n, int use_chol,
@@ -676,12 +831,20 @@ static int jacobi_cluster_enabled() {   // TNML_JACOBI_CLUSTER=0 keeps n <= 128 
 
 template <int E, int K>
 __global__ void k_jacobi_cluster(double*, double*, int*, int, double, double*, const double*, int, const int*);
+template <int E>
+__global__ void k_jacobi_cluster_w(double*, double*, int*, int, double, double*, const double*, int, const int*);
 
 static cudaError_t jacobi_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
   if (e != cudaSuccess) return e;
   // n = 512 uses a cluster of 16 CTAs (above the portable limit of 8)
-  return cudaFuncSetAttribute(k_jacobi_cluster<16, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  e = cudaFuncSetAttribute(k_jacobi_cluster<16, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 512 + 8) * 8);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_jacobi_cluster_w<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 256 + 8) * 8);
 }
 
 template <int E, int K>
@@ -700,6 +863,34 @@ static cudaError_t launch_cluster(int ctas, int threads, double* Wg, double* nrm
   cfg.numAttrs = 1;
   int max_sweeps = 60;
   return cudaLaunchKernelEx(&cfg, k_jacobi_cluster<E, K>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub);
+}
+
+template <int E>
+static cudaError_t launch_cluster_w(int ctas, int threads, double* Wg, double* nrm2g, int* flags, double tol,
+                                    double* info, const double* skip, int pass_id, const int* sub, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = (size_t)(threads / 128) * (8 * 32 * E + 8) * sizeof(double);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_sweeps = 60;
+  return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w<E>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub);
+}
+
+static int jacobi_variant() {   // TNML_JACOBI_VARIANT: 1 = one warp per rotation (default), 0 = register-blocked
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_JACOBI_VARIANT");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
 }
 
 struct JacobiBuffers {
@@ -746,13 +937,17 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
       k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id,
                                                               sub2, 0);
     }
-    e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    if (jacobi_variant()) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    else e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   } else {
     use_chol = 0;
     NP = n <= 256 ? 256 : 512;
     k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id, sub2,
                                                             0);
-    if (NP == 256) e = launch_cluster<8, 4>(8, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    if (jacobi_variant()) {
+      if (NP == 256) e = launch_cluster_w<8>(8, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+      else e = launch_cluster_w<16>(16, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    } else if (NP == 256) e = launch_cluster<8, 4>(8, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     else e = launch_cluster<16, 2>(16, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   }
   if (e != cudaSuccess) return TNML_CUDA_ERR(e);

@@ -108,6 +108,7 @@ class SweepEngine:
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
+        self.project_ctas = 110       # grid cap of the projection while the SVD runs beside it (0 = no cap)
         self._side = None
         self._inflight = None
 
@@ -136,7 +137,7 @@ class SweepEngine:
 
     def _side_stream(self):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)   # the SVD is on the critical path
         return self._side
 
     def _empty(self, n):
@@ -408,7 +409,7 @@ class SweepEngine:
         call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 6 * 8,
              _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec), 1 if L2_flag else 0, F64, st)
         self._inflight = (B, Bn, dB, G)
-        return dict(B=B, Bn=Bn, p=p, q=q, Dl=Dl, Dr=Dr, nB=nB, left_dir=left_dir, step=step, main=main, side=side)
+        return dict(B=B, Bn=Bn, G=G, p=p, q=q, Dl=Dl, Dr=Dr, nB=nB, left_dir=left_dir, step=step, main=main, side=side)
 
     def split_phase(self, ctx):
         """New prediction from the UN-truncated B' (NC:494-523) on the main stream, concurrently with the SVD split +
@@ -425,18 +426,21 @@ class SweepEngine:
         ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
         if side is not main:
             side.wait_stream(main)                      # B' is ready
-        with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
-            call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
-                 Dl, Dr, L, F64, st)
-        self.f_cur = 1 - self.f_cur
+        # the SVD is issued first: its kernels are short or small and should get SMs before the projection fills the GPU
         with torch.cuda.stream(side):
             with _Timed(self, "svd_split", 0.0):
                 call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), self.hist["svals"].data_ptr() +
                      step * self.hist["svals"].shape[1] * 8, _ptr(ws_svd), Dl, Dr, L, m, 1 if left_dir else 0,
                      self.svd_refine, F64, side.cuda_stream)
+        with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
+            # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
+            cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
+            call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
+                 Dl, Dr, L, cap, F64, st)
+        self.f_cur = 1 - self.f_cur
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
-            self._inflight = (self._inflight, ctx)      # keep alive until the main stream has passed the wait
+            self._inflight = ctx                        # keep B, B', G alive until the main stream has passed the wait
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

@@ -170,8 +170,13 @@ def test_projection(L, Ns, Dl, Dr, nl):
     f = empty(Ns, nl)
     ws = ws_for(L, "tnml_project_workspace_bytes", Ns, Dl, Dr, nl)
     L.call("tnml_project", dev(B).data_ptr(), dev(w).data_ptr(), dev(Le).data_ptr(), dev(Re).data_ptr(), f.data_ptr(),
-           ws.data_ptr(), Ns, Dl, Dr, nl, L.F64, st())
-    assert rel(f, O.project(B, Le, pa, pb, Re)) < TOL
+           ws.data_ptr(), Ns, Dl, Dr, nl, 0, L.F64, st())
+    want = O.project(B, Le, pa, pb, Re)
+    assert rel(f, want) < TOL
+    f2 = empty(Ns, nl)                         # capped grid (fewer sample splits): same result
+    L.call("tnml_project", _KEEP[-4].data_ptr(), _KEEP[-3].data_ptr(), _KEEP[-2].data_ptr(), _KEEP[-1].data_ptr(),
+           f2.data_ptr(), ws.data_ptr(), Ns, Dl, Dr, nl, 37, L.F64, st())
+    assert rel(f2, want) < TOL
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (1, 0), (0, 1), (1, 1)])
