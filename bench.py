@@ -268,11 +268,13 @@ def main():
         peak = float(pk["fp64_tflops_sustained"])
         peak_src = ("measured FP64 DMMA peak, tools/fp64_peak.cu on this pool's B200 (profiles/fp64_peak_r01.json); "
                     "MEASURED_PEAKS.json has no FP64 entry")
-    top = max(("grad", "project"), key=lambda k: kern.get(k, {}).get("ms_total", 0.0))
+    # k_grad: the K = Ns tensor-core reduction, the Ns-proportional kernel on the critical path (it has the whole GPU;
+    # k_project does the same FLOPs but is deliberately capped to ~110 SMs because it runs beside the SVD split)
+    top = "grad"
     traffic = None
     if os.path.exists(TRAFFIC_FILE):
         traffic = json.load(open(TRAFFIC_FILE)).get(top)
-    roofline = dict(kernel="k_" + top, bound="tensor", achieved=kern[top]["tflops"], peak=peak, unit="TFLOP/s",
+    roofline = dict(kernel="k_grad<FULL>", bound="tensor", achieved=kern[top]["tflops"], peak=peak, unit="TFLOP/s",
                     frac=kern[top]["tflops"] / peak, traffic=traffic, peak_source=peak_src,
                     flops_per_launch="8*Ns*L*Dl*Dr per launch (2 flops x Ns x (2 Dl) x (2 L Dr)), summed over the "
                                      "launches of the timed region / summed CUDA-event time")
