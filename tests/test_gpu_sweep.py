@@ -293,3 +293,29 @@ def test_cached_batch_attributes(tn):
     r = net.r_cum_contraction
     assert net.l_cum_contraction is None and len(r) == 6 and r[0] is f
     assert list(r[2].axes_names) == ['left', 'b'] and G.rel(r[2].elem.T, orc.env[2]) < 1e-13
+
+
+def test_config1_training_diagonals_trajectory(tn):
+    """training_diagonals.py re-enacted with np.random.seed(0); torch.manual_seed(0) and its default arguments
+    (S=64, M=10, L=2, 4000 train / 1000 validation samples, softmax + full_cross_ent, lr 0.01, weight decay 1,
+    5 epochs).  Expected values were recorded from the UNMODIFIED reference in the build container (SURVEY.md
+    section 8c(3)); five free-running sweeps are chaotic at the 1e-8 level, so the continuous quantities are compared
+    to 4-5 significant digits and the accuracies to the sample."""
+    import tensornetworkforml_b200.data_generator as gen
+    np.random.seed(0)
+    torch.manual_seed(0)
+    data, label = gen.create_dataset(5000, 8, 0.7)
+    train_loader, val_loader, _ = gen.prepare_dataset(data, label, 1, 0.2, train_batch_size=4000, val_batch_size=128,
+                                                      test_batch_size=128)
+    cal = next(iter(train_loader))
+    x_cal = np.array([c[0] for c in cal])
+    with quiet():
+        net = tn.Network(N=64, M=10, L=2, calibration_X=x_cal, normalize=True, act_fn="softmax", loss_fn="full_cross_ent")
+        val_acc, var_hist = net.train(train_loader, val_loader, lr=0.01, n_epochs=5, weight_dec=1)
+    assert abs(net.calibration_factor - 1.0151029521981736) < 1e-12
+    assert net.l_pos == 63 and var_hist.shape == (5, 2, 63)
+    assert np.abs(np.array(val_acc) - [0.91741, 0.99665, 0.99777, 0.99777, 0.99777]).max() < 2e-3
+    assert np.abs(var_hist[:, 0, 0] - [0.4925, 0.91375, 0.99725, 0.998, 0.99825]).max() < 1e-3
+    mae_first = [0.48637, 0.46678, 0.39598, 0.25410, 0.14638]
+    mae_last = [0.46746, 0.39696, 0.25564, 0.14706, 0.09181]
+    assert np.abs(var_hist[:, 1, 0] - mae_first).max() < 2e-4 and np.abs(var_hist[:, 1, -1] - mae_last).max() < 2e-4
