@@ -240,35 +240,46 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
   // permutation: the rows of R are simply scattered by pivot.
   if (use_chol) {
     constexpr int NG = NT / NP;                          // thread groups splitting the sum over previous rows (4)
+    constexpr int NWG = NP / 32;                         // warps of group 0 (they own the columns)
     __shared__ double part[NG][NP], diag[NP];
     __shared__ unsigned char active[NP];
     __shared__ int piv[NP];
-    __shared__ double piv_floor;
-    __shared__ int piv_idx;
-    for (int j = tid; j < NP; j += NT) { active[j] = j < n; diag[j] = j < n ? W[j * NP + j] : 0.0; }
+    __shared__ double cand_v[NWG];
+    __shared__ int cand_i[NWG];
+    __shared__ double piv_floor_s;
+    const int j = tid % NP, gq = tid / NP;
+    for (int jj = tid; jj < NP; jj += NT) { active[jj] = jj < n; diag[jj] = jj < n ? W[jj * NP + jj] : 0.0; }
     __syncthreads();
-    auto select_pivot = [&](bool first) {                // warp 0
-      double best = -1.0;
-      int bi = -1;
-      for (int j = lane; j < n; j += 32)
-        if (active[j]) { double v = diag[j]; if (v > best) { best = v; bi = j; } }
+    // per-warp pivot candidates: largest remaining diagonal entry (ties -> smallest index); every thread then
+    // reduces the NWG candidates itself, so the selection needs no barrier of its own
+    auto warp_candidate = [&]() {                        // warps of group 0 only
+      double best = active[j] ? diag[j] : -1.0;
+      int bi = active[j] ? j : -1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
       }
-      if (lane == 0) {
-        if (first) piv_floor = best * (double)n * 2.220446049250313e-16;
-        piv_idx = (bi >= 0 && best > piv_floor) ? bi : -1;
+      if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
+    };
+    auto pick = [&](double& best, int& bi) {
+      best = -1.0; bi = -1;
+#pragma unroll
+      for (int c = 0; c < NWG; ++c) {
+        const double v = cand_v[c];
+        const int i = cand_i[c];
+        if (i >= 0 && (bi < 0 || v > best)) { best = v; bi = i; }   // candidates come in increasing index order
       }
     };
-    if (warp == 0) select_pivot(true);
+    if (gq == 0) warp_candidate();
     __syncthreads();
-    const int j = tid % NP, gq = tid / NP;
+    double pbest; int c;
+    pick(pbest, c);
+    const double piv_floor = pbest * (double)n * 2.220446049250313e-16;
+    if (tid == 0) piv_floor_s = piv_floor;
     for (int k = 0; k < n; ++k) {
-      const int c = piv_idx;
-      if (c < 0) break;                                  // numerically rank deficient from here on
+      if (c < 0 || !(pbest > piv_floor)) break;          // numerically rank deficient from here on (uniform)
       // this group's share of sum_m R_m[c] R_m[j]; four accumulators: the FP64 FMA latency (~36 cycles) is what
       // bounds this loop, not its throughput
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
@@ -290,21 +301,25 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
         double scc = W[c * NP + c], sj = W[c * NP + j];
 #pragma unroll
         for (int g = 0; g < NG; ++g) { scc -= part[g][c]; sj -= part[g][j]; }
-        const double d = sqrt(fmax(scc, piv_floor));
+        scc = fmax(scc, piv_floor);
+        const double inv = rsqrt(scc);                   // one reciprocal square root instead of sqrt + division
         double r = 0.0;
-        if (j == c) r = d;
-        else if (active[j]) { r = sj / d; diag[j] = fma(-r, r, diag[j]); }
+        if (j == c) r = scc * inv;
+        else if (active[j]) { r = sj * inv; diag[j] = fma(-r, r, diag[j]); }
         W[c * NP + j] = r;
         if (j == c) { active[c] = 0; piv[k] = c; }
+        __syncwarp();
+        // (active[c] is only read by the warp that owns column c, which has just passed the __syncwarp)
+        warp_candidate();
       }
       __syncthreads();
-      if (warp == 0) select_pivot(false);
-      __syncthreads();
+      pick(pbest, c);
     }
     // Rows never eliminated (numerical rank deficiency): the Schur complement is below the resolution of this
     // pass.  Give them a tiny multiple of the unit vectors so that the sweeps still complete an orthonormal basis
     // (the second pass resolves the true small singular values inside that subspace).
-    const double tiny = sqrt(piv_floor);
+    __syncthreads();
+    const double tiny = sqrt(piv_floor_s);
     for (int e = tid; e < NP * NP; e += NT)
       if (active[e / NP]) W[e] = (e / NP == e % NP) ? tiny : 0.0;
     __syncthreads();
