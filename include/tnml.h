@@ -48,6 +48,11 @@ uint64_t tnml_kernel_launches(void);
 /* Human-readable text for a return code (static storage). */
 const char* tnml_error_string(int code);
 
+/* Page-lock a caller-owned HOST buffer in place (and release it), so the host->device copy of the input batch is a
+ * direct DMA transfer instead of a staged one.  Returns 0 (registered now), 1 (was already registered) or < 0. */
+int tnml_host_register(void* host_ptr, uint64_t bytes);
+int tnml_host_unregister(void* host_ptr);
+
 /* ---- a1: feature map + input packing ------------------------------------------------------------
  * tnml_feature_map   : phi[s][b][:] = [sin(pi x[b][s]/2), cos(pi x[b][s]/2)]  (sin first)   DG:165-167, NC:152-155
  * tnml_pack_features : X[b][s][:] (the (Ns,S,2) array the reference API takes) -> phi[s][b][:]   NC:222-225 */

@@ -20,6 +20,8 @@ SIGNATURES = {
     "tnml_version": (C.c_int, []),
     "tnml_kernel_launches": (C.c_uint64, []),
     "tnml_error_string": (C.c_char_p, [C.c_int]),
+    "tnml_host_register": (C.c_int, [_vp, C.c_uint64]),
+    "tnml_host_unregister": (C.c_int, [_vp]),
     "tnml_feature_map": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "tnml_pack_features": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "tnml_env_advance": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
@@ -69,6 +71,25 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = handle
     return _lib
+
+
+_registered = []        # host buffers page-locked in place by this process: [(ptr, nbytes)], most recent last
+
+
+def host_register(ptr: int, nbytes: int, keep: int = 3) -> bool:
+    """Page-lock [ptr, ptr+nbytes) once (process-wide LRU of ``keep`` buffers).  False if the driver refuses."""
+    key = (ptr, nbytes)
+    if key in _registered:
+        _registered.remove(key)
+        _registered.append(key)
+        return True
+    while len(_registered) >= keep:
+        old_ptr, _ = _registered.pop(0)
+        lib().tnml_host_unregister(old_ptr)
+    rc = lib().tnml_host_register(ptr, nbytes)
+    if rc == 0:
+        _registered.append(key)
+    return rc in (0, 1)
 
 
 def check(rc: int, what: str = ""):

@@ -37,6 +37,23 @@ extern "C" int tnml_contract(const void* T1, const void* T2, void* out, int64_t 
   return tnml_launch_status();
 }
 
+// Page-lock / release a caller-owned host buffer so that host->device copies from it are direct DMA transfers.
+// "Already registered" (by an earlier call or another component) counts as success; the error state is cleared.
+extern "C" int tnml_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return TNML_ERR_INVALID;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaSuccess) return TNML_OK;
+  cudaGetLastError();
+  return e == cudaErrorHostMemoryAlreadyRegistered ? 1 : TNML_CUDA_ERR(e);
+}
+
+extern "C" int tnml_host_unregister(void* ptr) {
+  if (!ptr) return TNML_ERR_INVALID;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) cudaGetLastError();
+  return TNML_OK;
+}
+
 unsigned long long g_tnml_kernel_launches = 0;
 extern "C" uint64_t tnml_kernel_launches(void) { return g_tnml_kernel_launches; }
 

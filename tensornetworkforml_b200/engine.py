@@ -104,7 +104,6 @@ class SweepEngine:
         self.y_dev = None
         self.hist = None
         self._pinned = None
-        self._registered = []         # host buffers page-locked in place: [(ptr, nbytes)]
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
@@ -117,23 +116,8 @@ class SweepEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _host_register(self, arr):
-        """cudaHostRegister the NumPy buffer once (keeps the last two distinct buffers registered)."""
-        ptr, nbytes = arr.ctypes.data, arr.nbytes
-        key = (ptr, nbytes)
-        if key in self._registered:
-            return True
-        rt = torch.cuda.cudart()
-        while len(self._registered) >= 2:
-            old_ptr, _ = self._registered.pop(0)
-            rt.cudaHostUnregister(old_ptr)
-        try:
-            err = rt.cudaHostRegister(ptr, nbytes, 0)
-        except Exception:
-            return False
-        if int(err) != 0:
-            return False
-        self._registered.append(key)
-        return True
+        """Page-lock the NumPy buffer in place (process-wide registry in _lib, survives engine re-creation)."""
+        return _lib.host_register(arr.ctypes.data, arr.nbytes)
 
     def _side_stream(self):
         if self._side is None:

@@ -17,7 +17,8 @@ def t(label, fn, n=3):
     for _ in range(n): r = fn()
     torch.cuda.synchronize(); print("%-34s %8.2f ms" % (label, (time.perf_counter() - t0) / n * 1e3)); return r
 t("load_input (H2D + pack) first", lambda: eng.load_input(X), 1)
-print("registered:", eng._registered[:1], "pinned staging:", None if eng._pinned is None else eng._pinned.numel())
+from tensornetworkforml_b200 import _lib
+print("registered:", _lib._registered[:1], "pinned staging:", None if eng._pinned is None else eng._pinned.numel())
 t("load_input (H2D + pack)", lambda: eng.load_input(X))
 t("engine.forward", lambda: eng.forward())
 t("Network.forward(X)", lambda: net.forward(X))
