@@ -10,8 +10,16 @@
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and keeps no
  *    global state: the caller owns every buffer, including workspaces sized by the *_workspace_bytes queries.
  *  - return value: 0 = ok; TNML_ERR_* (< 0) for argument errors; -(1000 + cudaError_t) for CUDA launch errors.
- *  - dtype: TNML_F64 is the parity path (FP64, DMMA tensor cores).  TNML_F32 is declared for the FP32/TF32
- *    variant and currently returns TNML_ERR_UNSUPPORTED.
+ *  - dtype: TNML_F64 is the parity path (FP64, DMMA tensor cores).  TNML_F32 is the FP32/TF32 variant: the PER-SAMPLE
+ *    arrays (phi, env, f, q, pp and the weight operand Wt / A_label handed to tnml_env_advance / tnml_site_predict, see
+ *    tnml_site_weights_f32 / tnml_convert_f32) are FP32, the tile-aligned contractions run on tcgen05 tensor cores (kind::tf32, FP32 accumulation in TMEM; ragged
+ *    bond dimensions fall back to FP32 FMA kernels), while site tensors, bond tensors, the gradient sum dB, clipping
+ *    and the SVD split stay FP64.  Entry points that accept TNML_F32: tnml_feature_map / tnml_pack_features (x, X stay
+ *    FP64, phi is FP32), tnml_env_advance, tnml_site_predict, tnml_act_lossder, tnml_grad (dB FP64), tnml_project
+ *    (B FP64); every other entry point is batch-independent and FP64 only (TNML_ERR_UNSUPPORTED for TNML_F32).
+ *    With TNML_F32 the q buffer of tnml_act_lossder / tnml_grad holds the loss derivative g[Ns][L] followed, at the next
+ *    multiple of 4 elements, by a copy of pp[Ns][4] (Ns*L + 4*Ns + 4 floats): the gradient is then the GEMM
+ *    dB = sum_b (g L)(x)(pp R) of two Khatri-Rao operands formed on the fly.
  *
  * Device layouts ("canonical"), all row-major, d = 2 physical components:
  *    phi   [S][Ns][2]        feature-mapped input, site-major
@@ -156,6 +164,16 @@ int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, vo
 int64_t tnml_svd_workspace_bytes(int32_t R, int32_t C);
 int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* ws, int32_t R, int32_t C, int32_t m, int32_t refine,
              int32_t dtype, tnml_stream_t stream);
+
+/* Weight operands of the TNML_F32 variant.
+ * tnml_convert_f32      : plain FP64 -> FP32 copy (label site for tnml_site_predict).
+ * tnml_site_weights_f32 : the W operand of tnml_env_advance(TNML_F32), K-major for the tcgen05 kernel:
+ *                         Wt[sigma][m][k] (FP32) with W[k][sigma][m] as defined above, straight from the FP64 site
+ *                         [Dl][2][Dr]: right-moving (K = Dl, M = Dr) Wt[sigma][c][a]; left-moving (K = Dr, M = Dl)
+ *                         Wt[sigma][a][c].  (kind::tf32 only multiplies K-major shared-memory operands correctly.) */
+int tnml_convert_f32(const void* src_f64, void* dst_f32, int64_t n, tnml_stream_t stream);
+int tnml_site_weights_f32(const void* site_f64, void* Wt_f32, int32_t Dl, int32_t Dr, int32_t left_moving,
+                          tnml_stream_t stream);
 
 /* ---- label-site layout change between sweep directions: [a][s][l][c] <-> [a][l][s][c] ------------------- */
 int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32_t Dr, int32_t L, int32_t to_left_layout,

@@ -10,6 +10,9 @@ B200 through libtnml.so (see ``engine.SweepEngine``).  Additive keyword-only ext
   device, process_group                          CUDA device; torch.distributed group for sample sharding (each rank
                                                  feeds its own shard of the batch, dB and the metrics are all-reduced).
   svd_refine                                     second Jacobi pass (default on; full accuracy for small sing. values)
+  dtype='float64' | 'float32'                    per-sample arrays and contractions: FP64 (DMMA, the parity path) or FP32
+                                                 storage with TF32 tensor-core products on tcgen05 (bond-tensor algebra
+                                                 and the SVD split stay FP64)
 
 There is no CPU fallback: without a CUDA device or without libtnml.so the compute methods raise.
 """
@@ -52,7 +55,7 @@ class Network():
 
     def __init__(self, N, M, D=2, L=10, T=0.1, normalize=False, calibration_X=None, act_fn='linear',
                  loss_fn='cross_entropy', check=False, *, truncation='reference', max_bond=None, device=None,
-                 process_group=None, svd_refine=True):
+                 process_group=None, svd_refine=True, dtype='float64'):
         self.N, self.D, self.L, self.M, self.T = N, D, L, M, T
         if D != 2:
             raise NotImplementedError("the device kernels are written for the 2-component feature map (D=2)")
@@ -60,7 +63,9 @@ class Network():
         assert loss_fn in _LOSSES, "Please select a loss function between 'MSE', 'cross_entropy', 'full_cross_ent'"
         self.act_fn, self.loss_fn = act_fn, loss_fn
         self.l_pos = 0
-        self._opts = dict(truncation=truncation, max_bond=max_bond, svd_refine=bool(svd_refine))
+        if dtype not in ('float64', 'float32'):
+            raise ValueError("dtype must be 'float64' or 'float32'")
+        self._opts = dict(truncation=truncation, max_bond=max_bond, svd_refine=bool(svd_refine), dtype=dtype)
         self._device, self._group = device, process_group
         self._eng = None
         self._host_As = None          # list[Tensor]; authoritative when _host_fresh
@@ -113,7 +118,8 @@ class Network():
             from .engine import SweepEngine
             self._eng = SweepEngine(self.N, self.L, self.T, self.act_fn, self.loss_fn,
                                     rule=self._opts["truncation"], max_bond=self._opts["max_bond"],
-                                    device=self._device, group=self._group, svd_refine=self._opts["svd_refine"])
+                                    device=self._device, group=self._group, svd_refine=self._opts["svd_refine"],
+                                    dtype=self._opts.get("dtype", "float64"))
             self._upload()
         elif self._host_fresh and self._host_dirty:
             self._upload()
@@ -156,7 +162,7 @@ class Network():
         eng = self._engine()
         eng.load_input(X)
         f_dev = eng.forward()
-        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        out = Tensor(elem=f_dev.t().cpu().numpy().astype(np.float64), axes_names=['l', 'b'])
         self._last_f = out
         return out
 
@@ -209,7 +215,7 @@ class Network():
         for _ in range(self.N - 1):
             f_dev = eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
         self._after_steps(var_hist, debug, L2_flag)
-        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        out = Tensor(elem=f_dev.t().cpu().numpy().astype(np.float64), axes_names=['l', 'b'])
         self._last_f = out
         return out
 
@@ -219,7 +225,7 @@ class Network():
         if f is not None and f is not self._last_f:
             import torch
             host = np.ascontiguousarray(np.asarray(f.elem, dtype=np.float64).T)
-            eng.f_buf[eng.f_cur].copy_(torch.from_numpy(host.reshape(-1)))
+            eng.f_buf[eng.f_cur].copy_(torch.from_numpy(host.reshape(-1)))      # converts to the per-sample dtype
 
     def _after_steps(self, var_hist, debug, L2_flag):
         eng = self._eng
@@ -257,7 +263,7 @@ class Network():
             eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
         f_dev = eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
         self._after_steps(var_hist, debug, L2_flag)
-        out = Tensor(elem=f_dev.t().cpu().numpy(), axes_names=['l', 'b'])
+        out = Tensor(elem=f_dev.t().cpu().numpy().astype(np.float64), axes_names=['l', 'b'])
         self._last_f = out
         return out
 

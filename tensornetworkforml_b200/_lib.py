@@ -46,6 +46,8 @@ SIGNATURES = {
     "tnml_svd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_label_site_swap": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_contract": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
+    "tnml_convert_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "tnml_site_weights_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
 }
 
 

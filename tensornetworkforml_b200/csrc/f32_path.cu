@@ -1,0 +1,1015 @@
+// FP32 / TF32 variant of the Ns-proportional kernels (dtype == TNML_F32).
+//
+//   k_env_advance_tc   out = sum_sigma phi (E . W)            tcgen05.mma kind::tf32, A = E tile via TMA (K-major),
+//                                                              B = W via TMA (MN-major), accumulator in TMEM
+//   k_project_tc       f = B' . (L (x) pp (x) R)               A = L tile via TMA, B' label slices resident in shared
+//                                                              memory (TMA, MN-major), double-buffered TMEM accumulators,
+//                                                              contraction with pp (x) R fused in the epilogue
+//   k_grad_tc          dB = sum_b (g L) (x) (pp R)             K = Ns reduction; BOTH operands are Khatri-Rao products
+//                                                              formed on the fly by producer warps straight into the
+//                                                              128B-swizzled UMMA layout; static split-K, fixed-order
+//                                                              FP64 second stage (bitwise reproducible)
+// Ragged shapes (bond dimensions that are not multiples of 64 / 32) run on plain FP32 FMA kernels (k_*_simt), which are
+// also the cross-check of the tensor-core kernels in the tests (TNML_F32_FORCE_SIMT=1).
+#include <cstdlib>
+
+#include "f32_path.cuh"
+#include "umma.cuh"
+
+namespace tnml {
+namespace f32 {
+
+bool tensor_cores_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_F32_FORCE_SIMT");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
+}  // namespace f32
+
+// -----------------------------------------------------------------------------------------------------
+// TMA tensor map (driver entry point fetched through the runtime: no -lcuda at link time)
+// -----------------------------------------------------------------------------------------------------
+namespace umma {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tensor_map_f32(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return TNML_ERR_UNSUPPORTED;
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {ld_elems * sizeof(float)};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? TNML_OK : TNML_ERR_INVALID;
+}
+}  // namespace umma
+
+namespace f32 {
+using namespace umma;
+
+// =====================================================================================================
+// elementwise kernels
+// =====================================================================================================
+__global__ void __launch_bounds__(256) k_feature_map_f32(const double* __restrict__ x, float2* __restrict__ phi,
+                                                        int64_t Ns, int S) {
+  __shared__ double tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int64_t b = b0 + r;
+    int s = s0 + tx;
+    tile[r][tx] = (b < Ns && s < S) ? x[b * S + s] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int s = s0 + r;
+    int64_t b = b0 + tx;
+    if (b < Ns && s < S) {
+      double arg = 3.141592653589793 * tile[tx][r] / 2;
+      phi[(int64_t)s * Ns + b] = make_float2((float)sin(arg), (float)cos(arg));
+    }
+  }
+}
+
+// X[b][s][2] (FP64, what the reference API passes) -> phi[s][b][2] (FP32)
+__global__ void __launch_bounds__(256) k_pack_features_f32(const double2* __restrict__ X, float2* __restrict__ phi,
+                                                          int64_t Ns, int S) {
+  __shared__ double2 tile[32][33];
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  const int s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int64_t b = b0 + r;
+    int s = s0 + tx;
+    tile[r][tx] = (b < Ns && s < S) ? X[b * S + s] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int s = s0 + r;
+    int64_t b = b0 + tx;
+    if (b < Ns && s < S) {
+      const double2 v = tile[tx][r];
+      phi[(int64_t)s * Ns + b] = make_float2((float)v.x, (float)v.y);
+    }
+  }
+}
+
+// FP32 weight operand of the environment advance, K-major: Wt[sigma][m][k].
+//   right-moving (K = Dl, M = Dr): Wt[sigma][c][a] = site[a][sigma][c];   left-moving (K = Dr, M = Dl): Wt[sigma][a][c]
+__global__ void __launch_bounds__(256) k_site_weights_f32(const double* __restrict__ site, float* __restrict__ Wt, int Dl,
+                                                         int Dr, int left_moving) {
+  const int n = Dl * 2 * Dr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    int a, sg, c;
+    if (left_moving) { c = i % Dr; a = (i / Dr) % Dl; sg = i / (Dr * Dl); }
+    else { a = i % Dl; c = (i / Dl) % Dr; sg = i / (Dl * Dr); }
+    Wt[i] = (float)site[((int64_t)a * 2 + sg) * Dr + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_convert_f32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] = (float)src[i];
+}
+
+// activation / loss derivative / metrics: same arithmetic as the FP64 kernel (evaluated in double per sample, the
+// exponentials of an un-stabilised softmax at T = 0.1 overflow FP32 early), FP32 in and out.
+// g[b][l] = dloss, pp[b][st] = phi_p(sigma) phi_q(tau); a copy of pp is appended after g (operand of the gradient).
+__global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict__ f, const int* __restrict__ y,
+                                                        const float2* __restrict__ phi_p,
+                                                        const float2* __restrict__ phi_q, float* __restrict__ g,
+                                                        float* __restrict__ pp, double* __restrict__ partial, int64_t Ns,
+                                                        int L, int act, int loss, double T) {
+  __shared__ double red[2][256];
+  const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  double n_ok = 0.0, abs_err = 0.0;
+  if (b < Ns) {
+    const float* fb = f + b * L;
+    const int yb = y[b];
+    double denom = 1.0;
+    if (act == TNML_ACT_SOFTMAX) {
+      denom = 0.0;
+      for (int l = 0; l < L; ++l) denom += exp((double)fb[l] / T);
+    }
+    const float2 p = phi_p[b], r = phi_q[b];
+    const float4 w = make_float4(p.x * r.x, p.x * r.y, p.y * r.x, p.y * r.y);
+    double best = 0.0;
+    int arg = 0;
+    for (int l = 0; l < L; ++l) {
+      const double v = fb[l];
+      double fa;
+      if (act == TNML_ACT_LINEAR) fa = v;
+      else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));
+      else fa = exp(v / T) / denom;
+      if (l == 0 || fa > best) { best = fa; arg = l; }
+      const double yl = (l == yb) ? 1.0 : 0.0;
+      abs_err += fabs(yl - fa);
+      double gv;
+      if (loss == TNML_LOSS_MSE) gv = yl - fa;
+      else if (loss == TNML_LOSS_CROSS_ENTROPY) gv = (act == TNML_ACT_SOFTMAX) ? (yl - yl * fa) / T : yl / fa;
+      else gv = 1.0 / ((l == yb ? fa : fa - 1.0) + 1e-4);
+      g[b * L + l] = (float)gv;
+    }
+    n_ok = (arg == yb) ? 1.0 : 0.0;
+    reinterpret_cast<float4*>(pp)[b] = w;
+    reinterpret_cast<float4*>(g + ((Ns * L + 3) & ~(int64_t)3))[b] = w;   // the copy starts 16-byte aligned
+  }
+  red[0][threadIdx.x] = n_ok;
+  red[1][threadIdx.x] = abs_err;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + s];
+      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = red[0][0];
+    partial[2 * blockIdx.x + 1] = red[1][0];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_metrics_final_f32(const double* __restrict__ partial, int nblocks,
+                                                          double* __restrict__ metrics) {
+  __shared__ double red[2][256];
+  double a = 0.0, e = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; e += partial[2 * i + 1]; }
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = e;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; }
+}
+
+// f[b][l] = sum L[b][a] phi[b][s] A[a][s][l][c] R[b][c]; thin kernel (forward() calls it with Dl == 1 or Dr == 1)
+__global__ void __launch_bounds__(256) k_site_predict_f32(const float* __restrict__ Lenv, const float2* __restrict__ phi,
+                                                         const float* __restrict__ A, const float* __restrict__ Renv,
+                                                         float* __restrict__ f, int64_t Ns, int Dl, int Dr, int L) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Ns * L) return;
+  int64_t b = idx / L;
+  int l = (int)(idx % L);
+  float2 p = phi[b];
+  float sum = 0.f;
+  for (int a = 0; a < Dl; ++a) {
+    float la = Lenv[b * Dl + a];
+    const float* A0 = A + (((int64_t)a * 2 + 0) * L + l) * Dr;
+    const float* A1 = A + (((int64_t)a * 2 + 1) * L + l) * Dr;
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = 0; c < Dr; ++c) {
+      float r = Renv[b * Dr + c];
+      s0 = fmaf(A0[c], r, s0);
+      s1 = fmaf(A1[c], r, s1);
+    }
+    sum = fmaf(la, p.x * s0 + p.y * s1, sum);
+  }
+  f[idx] = sum;
+}
+
+// =====================================================================================================
+// FP32 FMA fall-backs for ragged shapes
+// =====================================================================================================
+// out[b][m] = sum_s phi[b][s] sum_k E[b][k] Wt[s][m][k].  CTA = 32 samples x 64 columns; thread = (column, 8 samples).
+__global__ void __launch_bounds__(256) k_env_advance_simt(const float* __restrict__ E, const float2* __restrict__ phi,
+                                                         const float* __restrict__ W, float* __restrict__ out,
+                                                         int64_t Ns, int K, int M) {
+  __shared__ float Es[32][65];
+  const int tid = threadIdx.x, mm = tid & 63, sg = tid >> 6;
+  const int64_t b0 = (int64_t)blockIdx.x * 32;
+  for (int mc = 0; mc < M; mc += 64) {
+    const int m = mc + mm;
+    float acc0[8], acc1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = 0.f;
+    for (int kc = 0; kc < K; kc += 64) {
+      __syncthreads();
+      for (int e = tid; e < 32 * 64; e += 256) {
+        const int r = e >> 6, k = e & 63;
+        const int64_t b = b0 + r;
+        Es[r][k] = (b < Ns && kc + k < K) ? E[b * K + kc + k] : 0.f;
+      }
+      __syncthreads();
+      const int kmax = min(64, K - kc);
+      if (m < M) {
+        for (int k = 0; k < kmax; ++k) {
+          const float w0 = W[(int64_t)m * K + kc + k], w1 = W[((int64_t)M + m) * K + kc + k];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float e = Es[sg * 8 + i][k];
+            acc0[i] = fmaf(e, w0, acc0[i]);
+            acc1[i] = fmaf(e, w1, acc1[i]);
+          }
+        }
+      }
+    }
+    if (m < M) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t b = b0 + sg * 8 + i;
+        if (b < Ns) {
+          const float2 p = phi[b];
+          out[b * M + m] = p.x * acc0[i] + p.y * acc1[i];
+        }
+      }
+    }
+  }
+}
+
+// partial dB of one sample chunk: thread = (a in tile of 8, c in tile of 32), labels in groups of 4.
+__global__ void __launch_bounds__(256) k_grad_simt(const float* __restrict__ g, const float* __restrict__ pp,
+                                                  const float* __restrict__ Lenv, const float* __restrict__ Renv,
+                                                  float* __restrict__ ws, int64_t Ns, int Dl, int Dr, int L, int c_tiles,
+                                                  int64_t chunk) {
+  __shared__ float Ls[32][8], Rs[32][33], Gs[32][4], Ps[32][4];
+  const int tid = threadIdx.x, ci = tid & 31, ai = tid >> 5;
+  const int ct = blockIdx.x % c_tiles, at = blockIdx.x / c_tiles;
+  const int a = at * 8 + ai, c = ct * 32 + ci;
+  const int64_t bstart = (int64_t)blockIdx.y * chunk, bend = min(Ns, bstart + chunk);
+  float* out = ws + (size_t)blockIdx.y * ((size_t)Dl * 4 * L * Dr);
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int64_t bb = bstart; bb < bend; bb += 32) {
+      __syncthreads();
+      {
+        const int r = tid >> 3, j = tid & 7;   // 32 x 8
+        const int64_t b = bb + r;
+        Ls[r][j] = (b < bend && at * 8 + j < Dl) ? Lenv[b * Dl + at * 8 + j] : 0.f;
+        if (j < 4) {
+          Gs[r][j] = (b < bend && l0 + j < L) ? g[b * L + l0 + j] : 0.f;
+          Ps[r][j] = (b < bend) ? pp[b * 4 + j] : 0.f;
+        }
+      }
+      for (int e = tid; e < 32 * 32; e += 256) {
+        const int r = e >> 5, j = e & 31;
+        const int64_t b = bb + r;
+        Rs[r][j] = (b < bend && ct * 32 + j < Dr) ? Renv[b * Dr + ct * 32 + j] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int r = 0; r < 32; ++r) {
+        const float x = Ls[r][ai] * Rs[r][ci];
+        const float p0 = Ps[r][0], p1 = Ps[r][1], p2 = Ps[r][2], p3 = Ps[r][3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xl = x * Gs[r][i];
+          acc[i][0] = fmaf(xl, p0, acc[i][0]);
+          acc[i][1] = fmaf(xl, p1, acc[i][1]);
+          acc[i][2] = fmaf(xl, p2, acc[i][2]);
+          acc[i][3] = fmaf(xl, p3, acc[i][3]);
+        }
+      }
+    }
+    if (a < Dl && c < Dr) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (l0 + i >= L) break;
+#pragma unroll
+        for (int st = 0; st < 4; ++st)
+          out[((((size_t)a * 2 + (st >> 1)) * L + l0 + i) * 2 + (st & 1)) * Dr + c] = acc[i][st];
+      }
+    }
+  }
+}
+
+// dB[e] = sum_i ws[i][e] in the fixed order i = 0 .. ks-1, accumulated in FP64
+__global__ void __launch_bounds__(256) k_grad_reduce_f32(const float* __restrict__ ws, double* __restrict__ dB, int64_t n,
+                                                        int ks) {
+  int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  double s = 0.0;
+  for (int i = 0; i < ks; ++i) s += (double)ws[(size_t)i * n + e];
+  dB[e] = s;
+}
+
+// f[b][l] = sum B'[a][st][l][c] L[b][a] pp[b][st] R[b][c]; CTA = 32 samples, thread = (sample, label lane of 8)
+__global__ void __launch_bounds__(256) k_project_simt(const float* __restrict__ Bf, const float* __restrict__ pp,
+                                                     const float* __restrict__ Lenv, const float* __restrict__ Renv,
+                                                     float* __restrict__ f, int64_t Ns, int Dl, int Dr, int L) {
+  __shared__ float Ls[32][17], Rs[32][65];
+  const int tid = threadIdx.x, bi = tid & 31, ll = tid >> 5;
+  const int64_t b0 = (int64_t)blockIdx.x * 32, b = b0 + bi;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float p[4] = {0.f, 0.f, 0.f, 0.f};
+  if (b < Ns) {
+    const float4 t = reinterpret_cast<const float4*>(pp)[b];
+    p[0] = t.x; p[1] = t.y; p[2] = t.z; p[3] = t.w;
+  }
+  for (int ac = 0; ac < Dl; ac += 16) {
+    for (int cc = 0; cc < Dr; cc += 64) {
+      __syncthreads();
+      for (int e = tid; e < 32 * 16; e += 256) {
+        const int r = e >> 4, j = e & 15;
+        Ls[r][j] = (b0 + r < Ns && ac + j < Dl) ? Lenv[(b0 + r) * Dl + ac + j] : 0.f;
+      }
+      for (int e = tid; e < 32 * 64; e += 256) {
+        const int r = e >> 6, j = e & 63;
+        Rs[r][j] = (b0 + r < Ns && cc + j < Dr) ? Renv[(b0 + r) * Dr + cc + j] : 0.f;
+      }
+      __syncthreads();
+      const int an = min(16, Dl - ac), cn = min(64, Dr - cc);
+      for (int a = 0; a < an; ++a) {
+        const float la = Ls[bi][a];
+        for (int st = 0; st < 4; ++st) {
+          const float w = la * p[st];
+          for (int c = 0; c < cn; ++c) {
+            const float x = w * Rs[bi][c];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int l = ll + 8 * i;
+              if (l < L)
+                acc[i] = fmaf(x, Bf[((((size_t)(ac + a) * 2 + (st >> 1)) * L + l) * 2 + (st & 1)) * Dr + cc + c], acc[i]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (b < Ns) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int l = ll + 8 * i;
+      if (l < L) f[b * L + l] = acc[i];
+    }
+  }
+}
+
+// =====================================================================================================
+// tcgen05 kernels
+// =====================================================================================================
+constexpr uint32_t ROW_BYTES = 128;           // one swizzle row: 32 floats
+constexpr uint32_t ATOM_BYTES = 1024;         // 8 rows
+
+// ---- environment advance ---------------------------------------------------------------------------------
+// Both operands are K-major (rows of 128 B along K, SWIZZLE_128B): kind::tf32 returned zeros for MN-major operands
+// on this hardware (probed with structured inputs), so the weights are handed over transposed, Wt[sigma][m][k].
+// CTA = one tile of 128 samples x one chunk of mcs output columns (both sigma planes -> N = 2 mcs).
+//   A = E tile [128][K]        : K/32 TMA boxes of 128 rows x 128 B
+//   B = Wt rows (sigma, m0..)  : K/32 x 2 TMA boxes of mcs rows x 128 B
+//   D (TMEM, 128 lanes x N columns): lane = sample; epilogue out[b][m] = phi.x D[m] + phi.y D[mcs + m]
+// Several CTAs are resident per SM (64 KB of shared memory at K = 64), which is what overlaps TMA, MMA and epilogue.
+__global__ void __launch_bounds__(128) k_env_advance_tc(const __grid_constant__ CUtensorMap mapE,
+                                                       const __grid_constant__ CUtensorMap mapW,
+                                                       const float2* __restrict__ phi, float* __restrict__ out,
+                                                       int64_t Ns, int K, int Mout, int mcs) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar_full, bar_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = 2 * mcs;
+  const int kchunks = K / 32;
+  uint8_t* Bs = smem;                                       // kchunks x (N rows x 128 B)
+  uint8_t* As = smem + (size_t)kchunks * N * ROW_BYTES;     // kchunks x (128 rows x 128 B)
+  const int64_t tile_row = (int64_t)blockIdx.x * 128;
+  const int m0 = blockIdx.y * mcs;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapE);
+    tma_prefetch_desc(&mapW);
+  }
+  if (warp == 1) tmem_alloc<128>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)(kchunks * (N + 128)) * ROW_BYTES;
+    mbar_expect_tx(&bar_full, bytes);
+    for (int kc = 0; kc < kchunks; ++kc) {
+      tma_load_2d(Bs + (size_t)kc * N * ROW_BYTES, &mapW, 32 * kc, m0, &bar_full);
+      tma_load_2d(Bs + ((size_t)kc * N + mcs) * ROW_BYTES, &mapW, 32 * kc, Mout + m0, &bar_full);
+      tma_load_2d(As + (size_t)kc * 128 * ROW_BYTES, &mapE, 32 * kc, (int)tile_row, &bar_full);
+    }
+    mbar_wait_bounded(&bar_full, 0);
+    fence_after_sync();
+    const uint32_t idesc = idesc_tf32(128, N, 0, 0);
+    const uint32_t a0 = smem_u32(As), b0 = smem_u32(Bs);
+    for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = smem_desc(a0 + kc * 128 * ROW_BYTES + ks * 32, 16, ATOM_BYTES);
+        const uint64_t bd = smem_desc(b0 + kc * N * ROW_BYTES + ks * 32, 16, ATOM_BYTES);
+        mma_tf32(tmem_base, ad, bd, idesc, (kc | ks) != 0);
+      }
+    }
+    mma_commit(&bar_done);
+  }
+  __syncwarp();
+  mbar_wait_bounded(&bar_done, 0);
+  __syncwarp();
+  fence_after_sync();
+
+  const int64_t b = tile_row + warp * 32 + lane;
+  const float2 p = (b < Ns) ? phi[b] : make_float2(0.f, 0.f);
+  const uint32_t tlane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int j = 0; j < mcs / 32; ++j) {
+    float v0[32], v1[32];
+    tmem_ld32(tlane + 32 * j, v0);
+    tmem_ld32(tlane + mcs + 32 * j, v1);
+    if (b < Ns) {
+      float4* dst = reinterpret_cast<float4*>(out + b * Mout + m0 + 32 * j);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(fmaf(p.x, v0[4 * i], p.y * v1[4 * i]), fmaf(p.x, v0[4 * i + 1], p.y * v1[4 * i + 1]),
+                             fmaf(p.x, v0[4 * i + 2], p.y * v1[4 * i + 2]), fmaf(p.x, v0[4 * i + 3], p.y * v1[4 * i + 3]));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  __syncwarp();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
+// ---- projection ---------------------------------------------------------------------------------------------
+// B' repacked to FP32 as Bp[l][cc][ac][st (4)][c (64)][a (64)]: one (label, c-chunk, a-chunk) slice is a 256 x 64 matrix
+// (N = (st, c) rows, K = a contiguous) = 64 KB, K-major for the UMMA.
+__global__ void __launch_bounds__(256) k_pack_bond_f32(const double* __restrict__ B, float* __restrict__ Bp, int Dl,
+                                                      int Dr, int L) {
+  const int a_chunks = Dl / 64, c_chunks = Dr / 64;
+  const int64_t n = (int64_t)Dl * 4 * L * Dr;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    int64_t r = i;
+    const int a = r & 63; r >>= 6;
+    const int c = r & 63; r >>= 6;
+    const int st = r & 3; r >>= 2;
+    const int ac = r % a_chunks; r /= a_chunks;
+    const int cc = r % c_chunks; r /= c_chunks;
+    const int l = (int)r;
+    Bp[i] = (float)B[((((size_t)(ac * 64 + a) * 2 + (st >> 1)) * L + l) * 2 + (st & 1)) * Dr + cc * 64 + c];
+  }
+}
+
+constexpr int PJ_THREADS = 192;                       // warp 0: TMA, warp 1: MMA + TMEM, warps 2-5: epilogue
+constexpr int PJ_NL = 2;                              // label slices resident per CTA
+constexpr uint32_t PJ_SLICE_BYTES = 64 * 256 * 4;     // 64 KB
+constexpr uint32_t PJ_ASTAGE_BYTES = 128 * 64 * 4;    // 32 KB
+constexpr uint32_t PJ_SMEM_BYTES = PJ_NL * PJ_SLICE_BYTES + 2 * PJ_ASTAGE_BYTES + 1024;
+
+__global__ void __launch_bounds__(PJ_THREADS, 1) k_project_tc(const __grid_constant__ CUtensorMap mapL,
+                                                             const __grid_constant__ CUtensorMap mapB,
+                                                             const float* __restrict__ pp, const float* __restrict__ Renv,
+                                                             float* __restrict__ fout, int64_t Ns, int Dr, int L,
+                                                             int a_chunks, int ac, int c_chunks, int tiles_per_cta,
+                                                             int64_t fpart_stride, int accumulate) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t b_full, a_full[2], a_empty[2], t_full[2], t_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* Bs = smem;
+  uint8_t* As = smem + PJ_NL * PJ_SLICE_BYTES;
+  const int cc = blockIdx.x % c_chunks, grp = blockIdx.x / c_chunks;
+  const int l0 = grp * PJ_NL, nlab = min(PJ_NL, L - l0);
+  const int ntiles_total = (int)((Ns + 127) / 128);
+  const int t0 = blockIdx.y * tiles_per_cta, t1 = min(ntiles_total, t0 + tiles_per_cta);
+
+  if (tid == 0) {
+    mbar_init(&b_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&mapL);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0 && t0 < t1) {
+      mbar_expect_tx(&b_full, (uint32_t)nlab * PJ_SLICE_BYTES);
+      for (int j = 0; j < nlab; ++j) {
+        const int slice = ((l0 + j) * c_chunks + cc) * a_chunks + ac;
+        for (int kc = 0; kc < 2; ++kc)
+          tma_load_2d(Bs + j * PJ_SLICE_BYTES + kc * 256 * ROW_BYTES, &mapB, 32 * kc, slice * 256, &b_full);
+      }
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int s = it & 1;
+        mbar_wait_bounded(&a_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&a_full[s], PJ_ASTAGE_BYTES);
+        for (int kc = 0; kc < 2; ++kc)
+          tma_load_2d(As + s * PJ_ASTAGE_BYTES + kc * 128 * ROW_BYTES, &mapL, ac * 64 + 32 * kc, t * 128, &a_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && t0 < t1) {
+      const uint32_t idesc = idesc_tf32(128, 256, 0, 0);
+      mbar_wait_bounded(&b_full, 0);
+      int cnt = 0;
+      for (int t = t0, it = 0; t < t1; ++t, ++it) {
+        const int s = it & 1;
+        mbar_wait_bounded(&a_full[s], (it >> 1) & 1);
+        for (int j = 0; j < nlab; ++j, ++cnt) {
+          const int buf = cnt & 1;
+          mbar_wait_bounded(&t_empty[buf], ((cnt >> 1) & 1) ^ 1);
+          fence_after_sync();
+          const uint32_t a0 = smem_u32(As + s * PJ_ASTAGE_BYTES), b0 = smem_u32(Bs + j * PJ_SLICE_BYTES);
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const uint64_t ad = smem_desc(a0 + (k8 >> 2) * 128 * ROW_BYTES + (k8 & 3) * 32, 16, ATOM_BYTES);
+            const uint64_t bd = smem_desc(b0 + (k8 >> 2) * 256 * ROW_BYTES + (k8 & 3) * 32, 16, ATOM_BYTES);
+            mma_tf32(tmem_base + buf * 256, ad, bd, idesc, k8 != 0);
+          }
+          mma_commit(&t_full[buf]);
+        }
+        mma_commit(&a_empty[s]);
+      }
+    }
+  } else {
+    const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+    int cnt = 0;
+    for (int t = t0; t < t1; ++t) {
+      const int64_t b = (int64_t)t * 128 + q * 32 + lane;
+      float r[64], p[4] = {0.f, 0.f, 0.f, 0.f};
+      if (b < Ns) {
+        const float4* rp = reinterpret_cast<const float4*>(Renv + b * Dr + cc * 64);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float4 v = rp[i];
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        const float4 pv = reinterpret_cast<const float4*>(pp)[b];
+        p[0] = pv.x; p[1] = pv.y; p[2] = pv.z; p[3] = pv.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) r[i] = 0.f;
+      }
+      for (int j = 0; j < nlab; ++j, ++cnt) {
+        const int buf = cnt & 1;
+        mbar_wait_bounded(&t_full[buf], (cnt >> 1) & 1);
+        __syncwarp();
+        fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256;
+        float total = 0.f;
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[32];
+            tmem_ld32(taddr + st * 64 + h * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              s0 = fmaf(v[i], r[h * 32 + i], s0);
+              s1 = fmaf(v[i + 1], r[h * 32 + i + 1], s1);
+            }
+          }
+          total = fmaf(p[st], s0 + s1, total);
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[buf]);
+        if (b < Ns) {
+          float* dst = fout + (size_t)cc * fpart_stride + b * L + l0 + j;
+          *dst = accumulate ? (*dst + total) : total;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  __syncwarp();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+__global__ void __launch_bounds__(256) k_fpart_reduce_f32(const float* __restrict__ fpart, float* __restrict__ f,
+                                                         int64_t n, int parts, int accumulate) {
+  int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  float s = accumulate ? f[e] : 0.f;
+  for (int i = 0; i < parts; ++i) s += fpart[(size_t)i * n + e];
+  f[e] = s;
+}
+
+// ---- gradient ------------------------------------------------------------------------------------------------
+// CTA tile: a group of nlab <= 4 labels, a 64-slice of the left bond (a), a 64-slice of the right bond (c):
+//   D[(st, c)][(l', a)] = sum_b (pp[b][st] R[b][c]) (g[b][l'] L[b][a])        M = 256 (two UMMAs of 128), N = 64 nlab
+// Both operands are Khatri-Rao products that exist nowhere in memory: the 8 producer warps form them from R, pp, L, g
+// and write them straight into the K-major SWIZZLE_128B layout the UMMA reads (row = one (st, c) / (l', a) index,
+// 32 samples = 128 B per row and stage, 16-byte chunk index XOR (row & 7)); 3 stages of 32 samples.
+constexpr int GT_THREADS = 288;                         // warps 0-7: producers (0-3 also epilogue), warp 8: MMA + TMEM
+constexpr int GT_KB = 32, GT_STAGES = 3;
+constexpr uint32_t GT_OPER_BYTES = 256 * ROW_BYTES;     // 32 KB per operand and stage: 256 rows x 32 samples
+constexpr uint32_t GT_STAGE_BYTES = 2 * GT_OPER_BYTES;
+constexpr uint32_t GT_SMEM_BYTES = GT_STAGES * GT_STAGE_BYTES + 1024;
+
+__global__ void __launch_bounds__(GT_THREADS, 1) k_grad_tc(const float* __restrict__ g, const float* __restrict__ pp,
+                                                          const float* __restrict__ Lenv, const float* __restrict__ Renv,
+                                                          float* __restrict__ ws, int64_t Ns, int Dl, int Dr, int L,
+                                                          int ngroups, int a_chunks, int c_chunks, int64_t chunk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full[GT_STAGES], empty[GT_STAGES], done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int col = blockIdx.x;
+  const int cc = col % c_chunks; col /= c_chunks;
+  const int ac = col % a_chunks; col /= a_chunks;
+  const int grp = col;
+  // labels are spread as evenly as possible over the groups (10 labels -> 4 + 3 + 3)
+  const int base = L / ngroups, rem = L % ngroups;
+  const int l0 = grp * base + min(grp, rem), nlab = base + (grp < rem ? 1 : 0);
+  const int a0 = ac * 64, c0 = cc * 64;
+  const int64_t bstart = (int64_t)blockIdx.y * chunk, bend = min(Ns, bstart + chunk);
+  const int nkb = bend > bstart ? (int)((bend - bstart + GT_KB - 1) / GT_KB) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < GT_STAGES; ++i) {
+      mbar_init(&full[i], 8);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(&done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc<512>(&tmem_base_s);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(128, 64 * nlab, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % GT_STAGES;
+        mbar_wait_bounded(&full[s], (kb / GT_STAGES) & 1);
+        fence_after_sync();
+        const uint32_t as = smem_u32(smem + s * GT_STAGE_BYTES), bs = as + GT_OPER_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t bd = smem_desc(bs + ks * 32, 16, ATOM_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t ad = smem_desc(as + h * 128 * ROW_BYTES + ks * 32, 16, ATOM_BYTES);
+            mma_tf32(tmem_base + h * 256, ad, bd, idesc, (kb | ks) != 0);
+          }
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&done);
+    }
+  } else {
+    // ---- producers: thread -> column ci of the 64-wide slices (c for A, a for B), sample quads kq = kg and kg + 4
+    const int ci = tid & 63, kg = tid >> 6;
+    float rv[2][4], lv[2][4], gv[2][4][4];
+    float4 pv[2][4];
+    auto load = [&](int kb) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t b = bstart + (int64_t)kb * GT_KB + 4 * (kg + 4 * q) + i;
+          if (b < bend) {
+            rv[q][i] = Renv[b * Dr + c0 + ci];
+            lv[q][i] = Lenv[b * Dl + a0 + ci];
+            pv[q][i] = *reinterpret_cast<const float4*>(pp + b * 4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[q][i][j] = (j < nlab) ? g[b * L + l0 + j] : 0.f;
+          } else {
+            rv[q][i] = lv[q][i] = 0.f;
+            pv[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) gv[q][i][j] = 0.f;
+          }
+        }
+      }
+    };
+    if (nkb > 0) load(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % GT_STAGES;
+      mbar_wait_bounded(&empty[s], ((kb / GT_STAGES) & 1) ^ 1);
+      uint8_t* As = smem + s * GT_STAGE_BYTES;
+      uint8_t* Bs = As + GT_OPER_BYTES;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint32_t chunk16 = (uint32_t)(((kg + 4 * q) ^ (ci & 7)) << 4);    // row & 7 == ci & 7 (rows are 64 j + ci)
+        const float ps[4][4] = {{pv[q][0].x, pv[q][1].x, pv[q][2].x, pv[q][3].x},
+                                {pv[q][0].y, pv[q][1].y, pv[q][2].y, pv[q][3].y},
+                                {pv[q][0].z, pv[q][1].z, pv[q][2].z, pv[q][3].z},
+                                {pv[q][0].w, pv[q][1].w, pv[q][2].w, pv[q][3].w}};
+#pragma unroll
+        for (int st = 0; st < 4; ++st)
+          *reinterpret_cast<float4*>(As + (uint32_t)(st * 64 + ci) * ROW_BYTES + chunk16) =
+              make_float4(ps[st][0] * rv[q][0], ps[st][1] * rv[q][1], ps[st][2] * rv[q][2], ps[st][3] * rv[q][3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nlab)
+            *reinterpret_cast<float4*>(Bs + (uint32_t)(j * 64 + ci) * ROW_BYTES + chunk16) =
+                make_float4(gv[q][0][j] * lv[q][0], gv[q][1][j] * lv[q][1], gv[q][2][j] * lv[q][2],
+                            gv[q][3][j] * lv[q][3]);
+      }
+      if (kb + 1 < nkb) load(kb + 1);          // the next stage's global loads fly while the tensor core works
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    // ---- epilogue (warps 0-3): partial tile -> ws[split] in bond-tensor layout [a][sigma][l][tau][c] (FP32)
+    if (warp < 4) {
+      float* outp = ws + (size_t)blockIdx.y * ((size_t)Dl * 4 * L * Dr);
+      if (nkb > 0) {
+        mbar_wait_bounded(&done, 0);
+        fence_after_sync();
+      }
+      __syncwarp();
+      const int tau = warp >> 1, c = c0 + 32 * (warp & 1) + lane;
+      for (int h = 0; h < 2; ++h) {        // h = sigma
+        for (int j = 0; j < nlab; ++j) {
+#pragma unroll
+          for (int ah = 0; ah < 2; ++ah) {
+            float v[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + h * 256 + j * 64 + ah * 32, v);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int a = a0 + ah * 32 + i;
+              outp[((((size_t)a * 2 + h) * L + l0 + j) * 2 + tau) * Dr + c] = v[i];
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  __syncwarp();
+  if (warp == 8) tmem_dealloc<512>(tmem_base);
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+int feature_map(const double* x, float* phi, int64_t Ns, int S, cudaStream_t st) {
+  dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  TNML_COUNT(1);
+  k_feature_map_f32<<<grid, 256, 0, st>>>(x, (float2*)phi, Ns, S);
+  return tnml_launch_status();
+}
+
+int pack_features(const double* X, float* phi, int64_t Ns, int S, cudaStream_t st) {
+  dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
+  TNML_COUNT(1);
+  k_pack_features_f32<<<grid, 256, 0, st>>>((const double2*)X, (float2*)phi, Ns, S);
+  return tnml_launch_status();
+}
+
+int site_weights(const double* site, float* Wt, int Dl, int Dr, int left_moving, cudaStream_t st) {
+  TNML_COUNT(1);
+  k_site_weights_f32<<<min(tnml_cdiv(Dl * 2 * Dr, 256), 1024), 256, 0, st>>>(site, Wt, Dl, Dr, left_moving);
+  return tnml_launch_status();
+}
+
+int convert(const double* src, float* dst, int64_t n, cudaStream_t st) {
+  TNML_COUNT(1);
+  k_convert_f32<<<min(tnml_cdiv(n, 256), 2048), 256, 0, st>>>(src, dst, n);
+  return tnml_launch_status();
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int env_advance(const float* E, const float* phi, const float* W, float* out, int64_t Ns, int K, int M, cudaStream_t st) {
+  const bool tc = tensor_cores_enabled() && K % 32 == 0 && K <= 256 && M % 32 == 0 && aligned16(E) && aligned16(W) &&
+                  aligned16(out) && Ns < (1LL << 31);
+  TNML_COUNT(1);
+  if (!tc) {
+    k_env_advance_simt<<<tnml_cdiv(Ns, 32), 256, 0, st>>>(E, (const float2*)phi, W, out, Ns, K, M);
+    return tnml_launch_status();
+  }
+  const int mcs = (K <= 128 && M % 64 == 0) ? 64 : 32;
+  CUtensorMap mapE, mapW;
+  int rc = make_tensor_map_f32(&mapE, E, (uint64_t)Ns, (uint64_t)K, (uint64_t)K, 128);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&mapW, W, (uint64_t)2 * M, (uint64_t)K, (uint64_t)K, (uint32_t)mcs);
+  if (rc) return rc;
+  const size_t smem = (size_t)(2 * mcs / 32) * K * ROW_BYTES + (size_t)(K / 32) * 128 * ROW_BYTES + 1024;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_env_advance_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    smem_set = smem;
+  }
+  dim3 grid(tnml_cdiv(Ns, 128), M / mcs);
+  k_env_advance_tc<<<grid, 128, smem, st>>>(mapE, mapW, (const float2*)phi, out, Ns, K, M, mcs);
+  return tnml_launch_status();
+}
+
+int site_predict(const float* Lenv, const float* phi, const float* A, const float* Renv, float* f, int64_t Ns, int Dl,
+                 int Dr, int L, cudaStream_t st) {
+  TNML_COUNT(1);
+  k_site_predict_f32<<<tnml_cdiv(Ns * L, 256), 256, 0, st>>>(Lenv, (const float2*)phi, A, Renv, f, Ns, Dl, Dr, L);
+  return tnml_launch_status();
+}
+
+int act_lossder(const float* f, const int32_t* y, const float* phi_p, const float* phi_q, float* g, float* pp,
+                double* metrics, double* ws, int64_t Ns, int L, int act, int loss, double T, cudaStream_t st) {
+  const int nb = tnml_cdiv(Ns, 256);
+  TNML_COUNT(2);
+  k_act_lossder_f32<<<nb, 256, 0, st>>>(f, y, (const float2*)phi_p, (const float2*)phi_q, g, pp, ws, Ns, L, act, loss, T);
+  k_metrics_final_f32<<<1, 256, 0, st>>>(ws, nb, metrics);
+  return tnml_launch_status();
+}
+
+struct GradPlan {
+  bool tc;
+  int ngroups, a_chunks, c_chunks, cols, ks;
+  int64_t chunk;
+};
+
+static GradPlan grad_plan(int64_t Ns, int Dl, int Dr, int L) {
+  GradPlan p;
+  p.tc = tensor_cores_enabled() && Dl % 64 == 0 && Dr % 64 == 0;
+  if (p.tc) {
+    p.ngroups = tnml_cdiv(L, 4);
+    p.a_chunks = Dl / 64;
+    p.c_chunks = Dr / 64;
+    p.cols = p.ngroups * p.a_chunks * p.c_chunks;
+    int k = kNumSMs / p.cols;
+    const int kmax = tnml_cdiv(Ns, 4 * GT_KB);
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    p.chunk = tnml_align_up((Ns + k - 1) / k, GT_KB);
+    p.ks = tnml_cdiv(Ns, p.chunk);
+  } else {
+    p.ngroups = 1;
+    p.a_chunks = tnml_cdiv(Dl, 8);
+    p.c_chunks = tnml_cdiv(Dr, 32);
+    p.cols = p.a_chunks * p.c_chunks;
+    int k = 2 * kNumSMs / p.cols;
+    const int kmax = tnml_cdiv(Ns, 256);
+    if (k > kmax) k = kmax;
+    if (k < 1) k = 1;
+    p.chunk = tnml_align_up((Ns + k - 1) / k, 32);
+    p.ks = tnml_cdiv(Ns, p.chunk);
+  }
+  return p;
+}
+
+int64_t grad_workspace_bytes(int64_t Ns, int Dl, int Dr, int L) {
+  // sized for whichever kernel variant needs more partial tiles
+  const int64_t nB = (int64_t)Dl * 4 * L * Dr;
+  const GradPlan p = grad_plan(Ns, Dl, Dr, L);
+  return (int64_t)p.ks * nB * 4;
+}
+
+int grad(const float* g, const float* pp, const float* Lenv, const float* Renv, double* dB, void* ws, int64_t Ns, int Dl,
+         int Dr, int L, cudaStream_t st) {
+  const GradPlan p = grad_plan(Ns, Dl, Dr, L);
+  const int64_t nB = (int64_t)Dl * 4 * L * Dr;
+  TNML_COUNT(2);
+  if (p.tc) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
+      if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+      attr_set = true;
+    }
+    k_grad_tc<<<dim3(p.cols, p.ks), GT_THREADS, GT_SMEM_BYTES, st>>>(g, pp, Lenv, Renv, (float*)ws, Ns, Dl, Dr, L,
+                                                                      p.ngroups, p.a_chunks, p.c_chunks, p.chunk);
+  } else {
+    k_grad_simt<<<dim3(p.cols, p.ks), 256, 0, st>>>(g, pp, Lenv, Renv, (float*)ws, Ns, Dl, Dr, L, p.c_chunks, p.chunk);
+  }
+  k_grad_reduce_f32<<<tnml_cdiv(nB, 256), 256, 0, st>>>((const float*)ws, dB, nB, p.ks);
+  return tnml_launch_status();
+}
+
+static bool project_tc_ok(int Dl, int Dr) { return tensor_cores_enabled() && Dl % 64 == 0 && Dr % 64 == 0; }
+
+int64_t project_workspace_bytes(int64_t Ns, int Dl, int Dr, int L) {
+  const int64_t nB = (int64_t)Dl * 4 * L * Dr;
+  int64_t bytes = tnml_align_up(nB * 4, 1024);            // FP32 copy of B' (repacked on the tensor-core path)
+  if (project_tc_ok(Dl, Dr) && Dr > 64) bytes += (int64_t)(Dr / 64) * Ns * L * 4;
+  return bytes;
+}
+
+int project(const double* B, const float* pp, const float* Lenv, const float* Renv, float* f, void* ws, int64_t Ns,
+            int Dl, int Dr, int L, int max_ctas, cudaStream_t st) {
+  const int64_t nB = (int64_t)Dl * 4 * L * Dr;
+  float* Bf = (float*)ws;
+  if (!project_tc_ok(Dl, Dr) || !aligned16(Lenv) || !aligned16(Renv) || !aligned16(ws) || Ns >= (1LL << 31)) {
+    TNML_COUNT(2);
+    k_convert_f32<<<min(tnml_cdiv(nB, 256), 2048), 256, 0, st>>>(B, Bf, nB);
+    k_project_simt<<<tnml_cdiv(Ns, 32), 256, 0, st>>>(Bf, pp, Lenv, Renv, f, Ns, Dl, Dr, L);
+    return tnml_launch_status();
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PJ_SMEM_BYTES);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    attr_set = true;
+  }
+  const int a_chunks = Dl / 64, c_chunks = Dr / 64, ngroups = tnml_cdiv(L, PJ_NL);
+  float* fpart = (float*)((char*)ws + tnml_align_up(nB * 4, 1024));
+  TNML_COUNT(1);
+  k_pack_bond_f32<<<min(tnml_cdiv(nB, 256), 2048), 256, 0, st>>>(B, Bf, Dl, Dr, L);
+  CUtensorMap mapL, mapB;
+  int rc = make_tensor_map_f32(&mapL, Lenv, (uint64_t)Ns, (uint64_t)Dl, (uint64_t)Dl, 128);
+  if (rc) return rc;
+  rc = make_tensor_map_f32(&mapB, Bf, (uint64_t)L * c_chunks * a_chunks * 256, 64, 64, 256);
+  if (rc) return rc;
+  const int cols = ngroups * c_chunks;
+  const int budget = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+  const int ntiles = tnml_cdiv(Ns, 128);
+  int k = budget / cols;
+  if (k < 1) k = 1;
+  if (k > ntiles) k = ntiles;
+  const int tiles_per_cta = tnml_cdiv(ntiles, k);
+  const int ks = tnml_cdiv(ntiles, tiles_per_cta);
+  for (int ac = 0; ac < a_chunks; ++ac) {
+    TNML_COUNT(1);
+    if (c_chunks == 1) {
+      k_project_tc<<<dim3(cols, ks), PJ_THREADS, PJ_SMEM_BYTES, st>>>(mapL, mapB, pp, Renv, f, Ns, Dr, L, a_chunks, ac,
+                                                                      c_chunks, tiles_per_cta, 0, ac > 0);
+    } else {
+      k_project_tc<<<dim3(cols, ks), PJ_THREADS, PJ_SMEM_BYTES, st>>>(mapL, mapB, pp, Renv, fpart, Ns, Dr, L, a_chunks,
+                                                                      ac, c_chunks, tiles_per_cta, (int64_t)Ns * L, 0);
+      TNML_COUNT(1);
+      k_fpart_reduce_f32<<<tnml_cdiv(Ns * L, 256), 256, 0, st>>>(fpart, f, Ns * L, c_chunks, ac > 0);
+    }
+  }
+  return tnml_launch_status();
+}
+
+}  // namespace f32
+}  // namespace tnml

@@ -1,5 +1,6 @@
 // Feature map, input packing, environment advance (FP64 DMMA), forward's last contraction.
 #include "common.cuh"
+#include "f32_path.cuh"
 
 namespace tnml {
 
@@ -188,8 +189,9 @@ __global__ void __launch_bounds__(256) k_site_predict(const double* __restrict__
 using namespace tnml;
 
 extern "C" int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(x && phi && Ns > 0 && S > 0);
+  if (dtype == TNML_F32) return f32::feature_map((const double*)x, (float*)phi, Ns, S, (cudaStream_t)stream);
   dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
   TNML_COUNT(1);
   k_feature_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, (double2*)phi, Ns, S);
@@ -198,8 +200,9 @@ extern "C" int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S,
 
 extern "C" int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t S, int32_t dtype,
                                   tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(X && phi && Ns > 0 && S > 0);
+  if (dtype == TNML_F32) return f32::pack_features((const double*)X, (float*)phi, Ns, S, (cudaStream_t)stream);
   dim3 grid(tnml_cdiv(Ns, 32), tnml_cdiv(S, 32));
   TNML_COUNT(1);
   k_pack_features<<<grid, 256, 0, (cudaStream_t)stream>>>((const double2*)X, (double2*)phi, Ns, S);
@@ -208,8 +211,11 @@ extern "C" int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t 
 
 extern "C" int tnml_env_advance(const void* E, const void* phi_p, const void* W, void* out, int64_t Ns, int32_t K,
                                 int32_t M, int32_t dtype, tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(E && phi_p && W && out && Ns > 0 && K > 0 && M > 0);
+  if (dtype == TNML_F32)
+    return f32::env_advance((const float*)E, (const float*)phi_p, (const float*)W, (float*)out, Ns, K, M,
+                            (cudaStream_t)stream);
   TNML_COUNT(1);
   k_env_advance<<<tnml_cdiv(Ns, EA_BM), 128, 0, (cudaStream_t)stream>>>((const double*)E, (const double2*)phi_p,
                                                                        (const double*)W, (double*)out, Ns, K, M);
@@ -240,10 +246,24 @@ extern "C" int tnml_label_site_swap(const void* in, void* out, int32_t Dl, int32
 
 extern "C" int tnml_site_predict(const void* Lenv, const void* phi_p, const void* A_label, const void* Renv, void* f,
                                  int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(Lenv && phi_p && A_label && Renv && f && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
+  if (dtype == TNML_F32)
+    return f32::site_predict((const float*)Lenv, (const float*)phi_p, (const float*)A_label, (const float*)Renv,
+                             (float*)f, Ns, Dl, Dr, L, (cudaStream_t)stream);
   TNML_COUNT(1);
   k_site_predict<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>(
       (const double*)Lenv, (const double2*)phi_p, (const double*)A_label, (const double*)Renv, (double*)f, Ns, Dl, Dr, L);
   return tnml_launch_status();
+}
+
+extern "C" int tnml_convert_f32(const void* src_f64, void* dst_f32, int64_t n, tnml_stream_t stream) {
+  TNML_REQUIRE(src_f64 && dst_f32 && n > 0);
+  return f32::convert((const double*)src_f64, (float*)dst_f32, n, (cudaStream_t)stream);
+}
+
+extern "C" int tnml_site_weights_f32(const void* site_f64, void* Wt_f32, int32_t Dl, int32_t Dr, int32_t left_moving,
+                                     tnml_stream_t stream) {
+  TNML_REQUIRE(site_f64 && Wt_f32 && Dl > 0 && Dr > 0);
+  return f32::site_weights((const double*)site_f64, (float*)Wt_f32, Dl, Dr, left_moving, (cudaStream_t)stream);
 }

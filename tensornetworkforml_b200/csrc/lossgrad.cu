@@ -1,6 +1,7 @@
 // Activation + loss derivative + metrics (fused elementwise pass) and the gradient: a K = Ns reduction on
 // FP64 tensor cores (DMMA) with a static split-K and a fixed-order second stage.
 #include "common.cuh"
+#include "f32_path.cuh"
 
 namespace tnml {
 
@@ -267,9 +268,12 @@ extern "C" int64_t tnml_act_lossder_workspace_bytes(int64_t Ns) {
 extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const void* phi_q, void* q, void* pp,
                                 void* metrics, void* ws, int64_t Ns, int32_t L, int32_t act, int32_t loss, double T,
                                 int32_t dtype, tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(f && y && phi_p && phi_q && q && pp && metrics && ws && Ns > 0 && L > 0 && L <= AL_MAXL);
   TNML_REQUIRE(act >= 0 && act <= 2 && loss >= 0 && loss <= 2);
+  if (dtype == TNML_F32)
+    return f32::act_lossder((const float*)f, y, (const float*)phi_p, (const float*)phi_q, (float*)q, (float*)pp,
+                            (double*)metrics, (double*)ws, Ns, L, act, loss, T, (cudaStream_t)stream);
   int nb = tnml_cdiv(Ns, AL_THREADS);
   TNML_COUNT(1);
   k_act_lossder<<<nb, AL_THREADS, 0, (cudaStream_t)stream>>>((const double*)f, y, (const double2*)phi_p,
@@ -303,13 +307,19 @@ extern "C" int64_t tnml_grad_workspace_bytes(int64_t Ns, int32_t Dl, int32_t Dr,
   int cols, ks;
   int64_t chunk;
   grad_plan(Ns, Dl, Dr, L, &cols, &ks, &chunk);
-  return (int64_t)ks * Dl * 4 * L * Dr * 8;
+  const int64_t b64 = (int64_t)ks * Dl * 4 * L * Dr * 8, b32 = f32::grad_workspace_bytes(Ns, Dl, Dr, L);
+  return b64 > b32 ? b64 : b32;   // the query has no dtype argument: large enough for both variants
 }
 
 extern "C" int tnml_grad(const void* q, const void* Lenv, const void* Renv, void* dB, void* ws, int64_t Ns, int32_t Dl,
                          int32_t Dr, int32_t L, int32_t dtype, tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(q && Lenv && Renv && dB && ws && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
+  if (dtype == TNML_F32) {   // q = loss derivative [Ns][L] followed (16-byte aligned) by a copy of pp [Ns][4]
+    const float* g = (const float*)q;
+    return f32::grad(g, g + ((Ns * L + 3) & ~(int64_t)3), (const float*)Lenv, (const float*)Renv, (double*)dB, ws, Ns,
+                     Dl, Dr, L, (cudaStream_t)stream);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "f32_path.cuh"
 
 namespace tnml {
 
@@ -177,14 +178,18 @@ using namespace tnml;
 extern "C" int64_t tnml_project_workspace_bytes(int64_t Ns, int32_t Dl, int32_t Dr, int32_t L) {
   (void)Dl;
   int c_chunks = tnml_cdiv(Dr, 64);
-  return c_chunks > 1 ? (int64_t)c_chunks * Ns * L * 8 : 8;
+  const int64_t b64 = c_chunks > 1 ? (int64_t)c_chunks * Ns * L * 8 : 8, b32 = f32::project_workspace_bytes(Ns, Dl, Dr, L);
+  return b64 > b32 ? b64 : b32;   // the query has no dtype argument: large enough for both variants
 }
 
 extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Renv, void* f, void* ws,
                             int64_t Ns, int32_t Dl, int32_t Dr, int32_t L, int32_t max_ctas, int32_t dtype,
                             tnml_stream_t stream) {
-  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(B && pp && Lenv && Renv && f && ws && Ns > 0 && Dl > 0 && Dr > 0 && L > 0);
+  if (dtype == TNML_F32)
+    return f32::project((const double*)B, (const float*)pp, (const float*)Lenv, (const float*)Renv, (float*)f, ws, Ns,
+                        Dl, Dr, L, max_ctas, (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import F64, ACT, LOSS, call
+from ._lib import F64, F32, ACT, LOSS, call
 from .parallel import reduce_gradient_and_metrics
 
 
@@ -74,7 +74,7 @@ class _Timed:
 
 class SweepEngine:
     def __init__(self, S, L, T=0.1, act_fn="linear", loss_fn="cross_entropy", rule="reference", max_bond=None,
-                 device=None, group=None, svd_refine=True):
+                 device=None, group=None, svd_refine=True, dtype="float64"):
         if not torch.cuda.is_available():
             raise RuntimeError("tensornetworkforml_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.lib()
@@ -93,6 +93,15 @@ class SweepEngine:
         if group is not False and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.world = torch.distributed.get_world_size(self.group)
         self.svd_refine = 1 if svd_refine else 0
+        # dtype of the per-sample arrays (phi, environments, f, loss derivative): 'float64' = parity path (DMMA);
+        # 'float32' = FP32 storage with TF32 tensor-core products (tcgen05) and FP32 accumulation.  Site tensors,
+        # bond tensors, the gradient sum, clipping and the SVD split are FP64 in both modes.
+        if dtype not in ("float64", "float32"):
+            raise ValueError("dtype must be 'float64' or 'float32'")
+        self.dtype = dtype
+        self.DT = F64 if dtype == "float64" else F32
+        self.tdtype = torch.float64 if dtype == "float64" else torch.float32
+        self.esz = 8 if dtype == "float64" else 4
         self.sites = [None] * self.S
         self.bonds = [1] * (self.S + 1)
         self.l_pos = 0
@@ -126,6 +135,25 @@ class SweepEngine:
 
     def _empty(self, n):
         return torch.empty(int(n), dtype=torch.float64, device=self.device)
+
+    def _sample_empty(self, n):
+        return torch.empty(int(n), dtype=self.tdtype, device=self.device)
+
+    def _weights(self, t, key):
+        """Device pointer of a weight operand in the per-sample dtype (an FP32 copy in a workspace for 'float32')."""
+        if self.DT == F64:
+            return _ptr(t)
+        n = t.numel()
+        w = self._workspace(key, n * 4)
+        call("tnml_convert_f32", _ptr(t), _ptr(w), n, self._stream())
+        return _ptr(w)
+
+    def _site_weights(self, p, left_moving):
+        """FP32, K-major weight operand of the environment advance over plain site p (float32 variant)."""
+        Dl, Dr = self.bonds[p], self.bonds[p + 1]
+        w = self._workspace("w32", Dl * 2 * Dr * 4)
+        call("tnml_site_weights_f32", _ptr(self.sites[p]), _ptr(w), Dl, Dr, left_moving, self._stream())
+        return _ptr(w)
 
     def _workspace(self, key, nbytes):
         n = max(1, (int(nbytes) + 7) // 8)
@@ -188,15 +216,16 @@ class SweepEngine:
         cap = self._dcap()
         if self.env is None or self.Ns != Ns or self.env_cap < cap:
             self.env = None
-            self.env = torch.empty((self.S + 1, Ns * cap), dtype=torch.float64, device=self.device)
+            self.env = torch.empty((self.S + 1, Ns * cap), dtype=self.tdtype, device=self.device)
             self.env_cap = cap
             self.env[0, :Ns].fill_(1.0)
             self.env[self.S, :Ns].fill_(1.0)
-            self.f_buf = [self._empty(Ns * self.L), self._empty(Ns * self.L)]
-            self.q_buf = self._empty(Ns * self.L * 4)
-            self.pp_buf = self._empty(Ns * 4)
+            self.f_buf = [self._sample_empty(Ns * self.L), self._sample_empty(Ns * self.L)]
+            # float64: q = lossder * pp, (Ns, L, 4); float32: lossder (Ns, L) followed by an aligned copy of pp
+            self.q_buf = self._sample_empty(Ns * self.L * 4 if self.DT == F64 else Ns * self.L + 4 * Ns + 4)
+            self.pp_buf = self._sample_empty(Ns * 4)
         if self.phi is None or self.phi.numel() != self.S * Ns * 2:
-            self.phi = self._empty(self.S * Ns * 2)
+            self.phi = self._sample_empty(self.S * Ns * 2)
         self.Ns = Ns
 
     def load_input(self, X):
@@ -221,7 +250,7 @@ class SweepEngine:
                 Xd.copy_(pin, non_blocking=True)
         assert Xd.numel() == Ns * self.S * 2, "input must have shape (Ns, S, 2)"
         self._alloc_batch(Ns)
-        call("tnml_pack_features", _ptr(Xd), _ptr(self.phi), Ns, self.S, F64, self._stream())
+        call("tnml_pack_features", _ptr(Xd), _ptr(self.phi), Ns, self.S, self.DT, self._stream())
         self.h2d_bytes = Ns * self.S * 2 * 8
 
     def load_raw(self, x):
@@ -230,28 +259,34 @@ class SweepEngine:
             np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
         Ns = xd.shape[0]
         self._alloc_batch(Ns)
-        call("tnml_feature_map", _ptr(xd.contiguous()), _ptr(self.phi), Ns, self.S, F64, self._stream())
+        call("tnml_feature_map", _ptr(xd.contiguous()), _ptr(self.phi), Ns, self.S, self.DT, self._stream())
 
     def _phi(self, p):
-        return self.phi.data_ptr() + p * self.Ns * 2 * 8
+        return self.phi.data_ptr() + p * self.Ns * 2 * self.esz
 
     def _env(self, p):
-        return self.env.data_ptr() + p * self.env.shape[1] * 8
+        return self.env.data_ptr() + p * self.env.shape[1] * self.esz
 
     # ------------------------------------------------------------------ forward  (NC:195-258)
     def _advance_right(self, p):
         """env[p+1] = left env of sites <= p   (needs env[p], plain site p)."""
-        with _Timed(self, "env_advance", 4.0 * self.Ns * self.bonds[p] * self.bonds[p + 1]):
-            call("tnml_env_advance", self._env(p), self._phi(p), _ptr(self.sites[p]), self._env(p + 1), self.Ns,
-                 self.bonds[p], self.bonds[p + 1], F64, self._stream())
+        Dl, Dr = self.bonds[p], self.bonds[p + 1]
+        w = _ptr(self.sites[p]) if self.DT == F64 else self._site_weights(p, left_moving=0)
+        with _Timed(self, "env_advance", 4.0 * self.Ns * Dl * Dr):
+            call("tnml_env_advance", self._env(p), self._phi(p), w, self._env(p + 1), self.Ns, Dl, Dr, self.DT,
+                 self._stream())
 
     def _advance_left(self, p):
         """env[p] = right env of sites >= p   (needs env[p+1], plain site p)."""
         Dl, Dr = self.bonds[p], self.bonds[p + 1]
-        wt = self._workspace("wt", Dl * 2 * Dr * 8)
-        call("tnml_site_transpose", _ptr(self.sites[p]), _ptr(wt), Dl, Dr, F64, self._stream())
+        if self.DT == F64:
+            wt = self._workspace("wt", Dl * 2 * Dr * 8)
+            call("tnml_site_transpose", _ptr(self.sites[p]), _ptr(wt), Dl, Dr, F64, self._stream())
+            w = _ptr(wt)
+        else:
+            w = self._site_weights(p, left_moving=1)
         with _Timed(self, "env_advance", 4.0 * self.Ns * Dl * Dr):
-            call("tnml_env_advance", self._env(p + 1), self._phi(p), _ptr(wt), self._env(p), self.Ns, Dr, Dl, F64,
+            call("tnml_env_advance", self._env(p + 1), self._phi(p), w, self._env(p), self.Ns, Dr, Dl, self.DT,
                  self._stream())
 
     def forward(self):
@@ -266,8 +301,8 @@ class SweepEngine:
             raise Exception("forward should not be called if l has an intermediate position (l_pos=%d)" % l)
         self._label_to("R")
         f = self.f_buf[0]
-        call("tnml_site_predict", self._env(l), self._phi(l), _ptr(self.sites[l]), self._env(l + 1), _ptr(f), self.Ns,
-             self.bonds[l], self.bonds[l + 1], self.L, F64, self._stream())
+        call("tnml_site_predict", self._env(l), self._phi(l), self._weights(self.sites[l], "w32"), self._env(l + 1),
+             _ptr(f), self.Ns, self.bonds[l], self.bonds[l + 1], self.L, self.DT, self._stream())
         self.f_cur = 0
         return f.view(self.Ns, self.L)
 
@@ -378,12 +413,12 @@ class SweepEngine:
         dB, met = gbuf[:nB], gbuf[nB:nB + 4]
         ws = self._workspace("al", _lib.lib().tnml_act_lossder_workspace_bytes(Ns))
         call("tnml_act_lossder", _ptr(f_in), _ptr(self.y_dev), self._phi(p), self._phi(q), _ptr(self.q_buf),
-             _ptr(self.pp_buf), _ptr(met), _ptr(ws), Ns, L, self.act, self.loss, self.T, F64, st)
+             _ptr(self.pp_buf), _ptr(met), _ptr(ws), Ns, L, self.act, self.loss, self.T, self.DT, st)
         # gradient: K = Ns tensor-core reduction                                             NC:625-646, NC:710
         ws = self._workspace("grad", _lib.lib().tnml_grad_workspace_bytes(Ns, Dl, Dr, L))
         with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
-            call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L, F64,
-                 st)
+            call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L,
+                 self.DT, st)
         reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world)   # one collective per update
         self.hist["metrics"][step].copy_(met)
         # regularisation, clipping, update                                                   NC:728-761
@@ -420,7 +455,7 @@ class SweepEngine:
             # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
-                 Dl, Dr, L, cap, F64, st)
+                 Dl, Dr, L, cap, self.DT, st)
         self.f_cur = 1 - self.f_cur
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors

@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
     assert handle.tnml_version() >= 100
     assert handle.tnml_error_string(0) == b"ok"
     # pure host-side queries are safe without a GPU
-    assert handle.tnml_grad_workspace_bytes(60000, 64, 64, 10) == 14 * 64 * 4 * 10 * 64 * 8
+    # (the query has no dtype argument: it covers the FP64 split-K partials and the FP32 variant's)
+    assert handle.tnml_grad_workspace_bytes(60000, 64, 64, 10) >= 14 * 64 * 4 * 10 * 64 * 8
     assert handle.tnml_svd_split_workspace_bytes(64, 64, 10, 0) > 128 * 1280 * 8
 
 
