@@ -164,6 +164,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ns", type=int, default=CFG["Ns"], help="total samples (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f64 = the parity path (default, the BASELINE metric); f32 = FP32 storage / TF32 tcgen05 variant")
+    ap.add_argument("--D", type=int, default=CFG["D"], help="bond dimension (other BASELINE.json configs)")
+    ap.add_argument("--S", type=int, default=CFG["S"], help="number of sites (a square number)")
+    ap.add_argument("--L", type=int, default=CFG["L"], help="number of labels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -179,8 +184,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    c = dict(CFG, Ns=args.ns)
+    c = dict(CFG, Ns=args.ns, D=args.D, S=args.S, L=args.L)
     S, L, D, Ns = c["S"], c["L"], c["D"], c["Ns"]
+    default_cfg = (S, L, D) == (CFG["S"], CFG["L"], CFG["D"])
     X_all, y_all = synthetic_data(Ns, S, L, c["seed"])
     from tensornetworkforml_b200.parallel import shard_bounds
     lo, hi = shard_bounds(Ns, rank, world)
@@ -190,7 +196,8 @@ def main():
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
         net = tn.Network(N=S, M=D, L=L, normalize=True, calibration_X=X[:min(len(X), 2048)], act_fn=c["act"],
-                         loss_fn=c["loss"], truncation="fixed", max_bond=D, device="cuda:%d" % local_rank)
+                         loss_fn=c["loss"], truncation="fixed", max_bond=D, device="cuda:%d" % local_rank,
+                         dtype="float64" if args.dtype == "f64" else "float32")
     eng = net._engine()
     lib = _lib.lib()
 
@@ -274,7 +281,15 @@ def main():
     traffic = None
     if os.path.exists(TRAFFIC_FILE):
         traffic = json.load(open(TRAFFIC_FILE)).get(top)
-    roofline = dict(kernel="k_grad<FULL>", bound="tensor", achieved=kern[top]["tflops"], peak=peak, unit="TFLOP/s",
+    kname = "k_grad<FULL>"
+    if args.dtype == "f32":
+        # no measured TF32 peak on this pool: half of MEASURED_PEAKS.json's bf16 burst figure (TF32 runs at half the bf16
+        # rate on tcgen05; nominal 1.1 PFLOP/s dense)
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak = (json.load(open(mp))["bf16_tflops"] / 2) if os.path.exists(mp) else 1100.0
+        peak_src = "half of the measured bf16 burst peak in MEASURED_PEAKS.json (TF32 = bf16 / 2 on tcgen05); not measured directly"
+        kname, traffic = "k_grad_tc (tcgen05 kind::tf32)", None
+    roofline = dict(kernel=kname, bound="tensor", achieved=kern[top]["tflops"], peak=peak, unit="TFLOP/s",
                     frac=kern[top]["tflops"] / peak, traffic=traffic, peak_source=peak_src,
                     flops_per_launch="8*Ns*L*Dl*Dr per launch (2 flops x Ns x (2 Dl) x (2 L Dr)), summed over the "
                                      "launches of the timed region / summed CUDA-event time")
@@ -303,20 +318,24 @@ def main():
 
     line = dict(metric="bond_updates_per_s", value=value, unit="bond-updates/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps, s_per_sweep=ms / args.steps * 1e-3,
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="config3: 14x14 synthetic 10-label stripes, S=196 sites, L=10, D=64 (fixed-D "
-                                     "truncation), Ns=%d samples total, FP64, linear/MSE, L2 norm-environment term on"
-                                     % Ns, S=S, L=L, D=D, Ns=Ns, samples_per_gpu=hi - lo, parallelism="sample-shard x%d"
+                higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f64" if args.dtype == "f64" else "tf32 (fp32 storage, fp64 bond algebra + SVD)", data="synthetic",
+                config=dict(workload="%s: %dx%d synthetic %d-label stripes, S=%d sites, L=%d, D=%d (fixed-D "
+                                     "truncation), Ns=%d samples total, %s, linear/MSE, L2 norm-environment term on"
+                                     % ("config3" if default_cfg else "variant of config3", int(round(S ** 0.5)),
+                                        int(round(S ** 0.5)), L, S, L, D, Ns,
+                                        "FP64" if args.dtype == "f64" else "FP32/TF32"),
+                            S=S, L=L, D=D, Ns=Ns, samples_per_gpu=hi - lo, parallelism="sample-shard x%d"
                                      % world, l2_flush="inputs exceed L2 (env cache %.1f GB per GPU)" %
-                                     (eng.env.numel() * 8 / 1e9), bond_updates_per_step=S - 1),
+                                     (eng.env.numel() * eng.esz / 1e9), bond_updates_per_step=S - 1),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, kernels=kern,
                 finite=finite, bonds_mid=eng.bond_dims()[S // 2], jacobi_sweeps=jacobi_sweeps, spectrum=spectrum)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = cpu_bond_updates(1, 3, Ns, D, L, c["lr"], c["wd"], c["act"], c["loss"])
         per = float(np.mean(times))
         line["cpu_baseline"] = dict(value=1.0 / per, unit="bond-updates/s", cores=host_threads(), kind="port",
-                                    sample="3 interior bond updates (D=64 both sides, L=10) at the full Ns=%d with the "
-                                           "NumPy/OpenBLAS oracle port of sweep_step (1 warm-up update)" % Ns,
+                                    sample="3 interior bond updates (D=%d both sides, L=%d) at the full Ns=%d with the "
+                                           "NumPy/OpenBLAS oracle port of sweep_step (1 warm-up update)" % (D, L, Ns),
                                     s_per_sweep_extrapolated=per * (S - 1))
     if rank == 0:
         print(json.dumps(line))

@@ -746,6 +746,185 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w(double* __restrict__ W
   if (gwarp == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cluster version 3: blocks of EIGHT rows, one CTA-resident group of 8 warps per block pair, one rotation per warp.
+// Compared with version 2 (blocks of 4) a sweep has the same n - 1 sequential rotation sets but half the block-rounds,
+// i.e. half the L2 round trips (write back, cluster barrier, reload ~ 1900 cycles) that separate them.
+// Mixed-precision inner products: while the previous sweep still saw a pair with a relative inner product above 1e-2
+// the rotation angle only has to be roughly right, so the dot product is accumulated and butterfly-reduced in FP32
+// (4-cycle FMAs and one shuffle per stage instead of 36-cycle FP64 operations and two shuffles); the rotation itself
+// is still applied to the FP64 rows with an exactly renormalised (cos, sin), so the singular values are untouched.
+// The last sweeps (quadratic convergence from 1e-2 down to eps) run entirely in FP64.
+// flags[sweep]: bit 0 = some pair was above 1e-8, bit 1 = some pair was above 1e-2.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pair_barrier256(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+template <int E, bool FAST>
+__device__ __forceinline__ int rotate_pair2(double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ nx,
+                                            double* __restrict__ ny, double tol2, int lane) {
+  double x[E], y[E];
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    x[k] = rx[lane + 32 * k];
+    y[k] = ry[lane + 32 * k];
+  }
+  const double al = *nx, be = *ny;
+  const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
+  const double sc = __hiloint2double((2046 - ex) << 20, 0);  // 2^(1023-ex): (al+be)*sc in [1,2)
+  const float df = (float)((be - al) * sc);
+  double ga;
+  float tf;
+  if constexpr (FAST) {
+    // the rows are scaled by hs = 2^floor((1023-ex)/2) ~ (al+be)^(-1/2) before the conversion, so that graded rows
+    // stay inside the FP32 range; hs^2 = sc (even exponent) or sc / 2 (odd)
+    const int hexp = (1023 - ex) >> 1;
+    const double hs = __hiloint2double((1023 + hexp) << 20, 0);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const float xf = (float)(x[k] * hs), yf = (float)(y[k] * hs);
+      if (k & 1) a1 = fmaf(xf, yf, a1);
+      else a0 = fmaf(xf, yf, a0);
+    }
+    float gf = a0 + a1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gf += __shfl_xor_sync(0xffffffffu, gf, o);
+    gf *= ((1023 - ex) & 1) ? 2.0f : 1.0f;                        // gf = ga * sc
+    tf = gf + gf;
+    ga = (double)gf * __hiloint2double(ex << 20, 0);              // ga = gf / sc = gf * 2^(ex-1023)
+  } else {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      if (k & 1) a1 = fma(x[k], y[k], a1);
+      else a0 = fma(x[k], y[k], a0);
+    }
+    ga = warp_sum(a0 + a1);
+    tf = (float)((ga + ga) * sc);
+  }
+  const double g2 = ga * ga, ab = al * be;
+  const double thr = (FAST ? 1e-12 : tol2) * ab;
+  if (!(g2 > thr) || ex == 0 || ex >= 2040) return 0;
+  const float hh = fmaf(df, df, tf * tf);
+  const float h = hh * rsqrt_approx(hh);
+  const float t0 = __fdividef(tf, df + copysignf(h, df));
+  const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
+  double cs = (double)cf, sn = (double)(cf * t0);
+  const double e = fma(cs, cs, fma(sn, sn, -1.0));
+  const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
+  cs *= nu;
+  sn *= nu;
+#pragma unroll
+  for (int k = 0; k < E; ++k) {
+    rx[lane + 32 * k] = fma(cs, x[k], -sn * y[k]);
+    ry[lane + 32 * k] = fma(sn, x[k], cs * y[k]);
+  }
+  if (lane == 0) {
+    const double tg = (double)t0 * ga;
+    *nx = al - tg;
+    *ny = be + tg;
+  }
+  return (g2 > 1e-16 * ab ? 1 : 0) | (g2 > 1e-4 * ab ? 2 : 0);   // bit 0: above 1e-8, bit 1: above 1e-2
+}
+
+template <int E>
+__global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ Wg, double* __restrict__ nrm2g,
+                                                           int* __restrict__ flags, int max_sweeps, double tol,
+                                                           double* __restrict__ info, const double* __restrict__ skip_flag,
+                                                           int pass_id, const int* __restrict__ sub, int mixed) {
+  constexpr int NP = 32 * E, K = 8, NBmax = NP / K;
+  extern __shared__ __align__(16) double sm[];   // per block pair: 16 rows x NP, then 16 norms
+  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  int NB = NBmax;
+  if (sub) {
+    const int nact = sub[0];
+    if (nact == 0) return;
+    NB = 2 * ((((nact + K - 1) / K) + 1) / 2);
+    if (NB < 2) NB = 2;
+    if (NB > NBmax) NB = NBmax;
+  }
+  const int TW = NB / 2;                                          // active block pairs per block-round
+  cg::cluster_group cl = cg::this_cluster();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bpl = warp >> 3, w = warp & 7;                        // local block pair, role inside the pair
+  const int bpc = blockDim.x >> 8;                                // block pairs per CTA
+  const int bp = (int)cl.block_rank() * bpc + bpl;                // global block pair index
+  const int gwarp = (int)cl.block_rank() * (blockDim.x >> 5) + warp, nwarps = (int)cl.num_blocks() * (blockDim.x >> 5);
+  const bool active = bp < TW;
+  double* rows = sm + (size_t)bpl * (16 * NP + 16);
+  double* nr = rows + 16 * NP;
+  const double tol2 = tol * tol;
+  int ra = (bp == 0) ? 0 : bp - 1, rb = NB - 2 - bp;
+  int sweeps_done = 0;
+  bool fast = mixed != 0;
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = gwarp; r < NB * K; r += nwarps) {   // refresh the cached squared row norms
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const double v = __ldcg(Wg + (size_t)r * NP + lane + 32 * k); s = fma(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) nrm2g[r] = s;
+    }
+    cl.sync();
+    int rotated = 0;
+    for (int round = 0; round < NB - 1; ++round) {
+      if (active) {
+        const int bi = (bp == 0) ? 0 : 1 + ra;
+        const int bj = 1 + rb;
+        // stage: warp w brings row w of each block (rows 0-7 = block bi, 8-15 = block bj)
+        double* const ga_ = Wg + (size_t)(K * bi + w) * NP + lane;
+        double* const gb_ = Wg + (size_t)(K * bj + w) * NP + lane;
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          rows[w * NP + lane + 32 * k] = __ldcg(ga_ + 32 * k);
+          rows[(8 + w) * NP + lane + 32 * k] = __ldcg(gb_ + 32 * k);
+        }
+        if (lane == 0) { nr[w] = __ldcg(nrm2g + K * bi + w); nr[8 + w] = __ldcg(nrm2g + K * bj + w); }
+        pair_barrier256(1 + bpl);
+        if (round == 0) {   // the 28 pairs inside each block, once per sweep: round-robin of 8 players, 7 sets
+          const int base = (w >> 2) * 8, j = w & 3;
+#pragma unroll 1
+          for (int s = 0; s < 7; ++s) {
+            int p, q;
+            if (j == 0) { p = 7; q = s; }
+            else { p = (s + j) % 7; q = (s - j + 7) % 7; }
+            rotated |= fast ? rotate_pair2<E, true>(rows + (base + p) * NP, rows + (base + q) * NP, nr + base + p,
+                                                    nr + base + q, tol2, lane)
+                            : rotate_pair2<E, false>(rows + (base + p) * NP, rows + (base + q) * NP, nr + base + p,
+                                                     nr + base + q, tol2, lane);
+            pair_barrier256(1 + bpl);
+          }
+        }
+#pragma unroll 1
+        for (int s = 0; s < 8; ++s) {   // the 64 pairs across the two blocks: warp w rotates (w, 8 + (w+s)%8)
+          const int q = 8 + ((w + s) & 7);
+          rotated |= fast ? rotate_pair2<E, true>(rows + w * NP, rows + q * NP, nr + w, nr + q, tol2, lane)
+                          : rotate_pair2<E, false>(rows + w * NP, rows + q * NP, nr + w, nr + q, tol2, lane);
+          pair_barrier256(1 + bpl);
+        }
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          ga_[32 * k] = rows[w * NP + lane + 32 * k];
+          gb_[32 * k] = rows[(8 + w) * NP + lane + 32 * k];
+        }
+        if (lane == 0) { nrm2g[K * bi + w] = nr[w]; nrm2g[K * bj + w] = nr[8 + w]; }
+        ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+        rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+      }
+      cl.sync();
+    }
+    if (fast) rotated |= 1;                                        // an FP32 sweep never certifies convergence
+    if (rotated && lane == 0) atomicOr(flags + sweep, rotated);
+    sweeps_done = sweep + 1;
+    cl.sync();
+    const int any = __ldcg(flags + sweep);
+    if (!(any & 1)) break;
+    fast = mixed != 0 && (any & 2) != 0;                           // FP32 inner products while some pair is above 1e-2
+  }
+  if (gwarp == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
+}
+
 // Ranking + normalisation after the cluster sweeps (one CTA): squared row norms rank the rows (descending, ties
 // by index); Vt[k] = k-th unit row, lam[k] = eigenvalue of the Gram matrix; sets the second-pass skip flag.
 __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict__ Wg, int NP, int n, int use_chol,
@@ -848,6 +1027,8 @@ template <int E, int K>
 __global__ void k_jacobi_cluster(double*, double*, int*, int, double, double*, const double*, int, const int*);
 template <int E>
 __global__ void k_jacobi_cluster_w(double*, double*, int*, int, double, double*, const double*, int, const int*);
+template <int E>
+__global__ void k_jacobi_cluster_w8(double*, double*, int*, int, double, double*, const double*, int, const int*, int);
 
 static cudaError_t jacobi_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
@@ -859,7 +1040,13 @@ static cudaError_t jacobi_prepare() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_jacobi_cluster_w<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 512 + 8) * 8);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_jacobi_cluster_w<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 256 + 8) * 8);
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 256 + 8) * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 512 + 16) * 8);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_jacobi_cluster_w8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 256 + 16) * 8);
 }
 
 template <int E, int K>
@@ -899,11 +1086,36 @@ static cudaError_t launch_cluster_w(int ctas, int threads, double* Wg, double* n
   return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w<E>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub);
 }
 
-static int jacobi_variant() {   // TNML_JACOBI_VARIANT: 1 = one warp per rotation (default), 0 = register-blocked
+template <int E>
+static cudaError_t launch_cluster_w8(int ctas, int threads, double* Wg, double* nrm2g, int* flags, double tol,
+                                     double* info, const double* skip, int pass_id, const int* sub, int mixed,
+                                     cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = (size_t)(threads / 256) * (16 * 32 * E + 16) * sizeof(double);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_sweeps = 60;
+  return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w8<E>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub,
+                            mixed);
+}
+
+// TNML_JACOBI_VARIANT: 2 = blocks of 8 rows, FP64 inner products (default); 3 = same + FP32 inner products in the early
+// sweeps (measured on B200: saves ~20 % per sweep but costs one more sweep, 1.35 ms against 1.25 ms per split, so it is
+// off); 1 = blocks of 4 rows, one warp per rotation (1.41 ms); 0 = register-blocked
+static int jacobi_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("TNML_JACOBI_VARIANT");
-    v = (e && atoi(e) == 0) ? 0 : 1;
+    v = e ? atoi(e) : 2;
+    if (v < 0 || v > 3) v = 2;
   }
   return v;
 }
@@ -952,14 +1164,20 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
       k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id,
                                                               sub2, 0);
     }
-    if (jacobi_variant()) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
+    const int jv = jacobi_variant();
+    if (jv >= 2) e = launch_cluster_w8<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+    else if (jv == 1) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     else e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   } else {
     use_chol = 0;
     NP = n <= 256 ? 256 : 512;
     k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id, sub2,
                                                             0);
-    if (jacobi_variant()) {
+    const int jv = jacobi_variant();
+    if (jv >= 2) {
+      if (NP == 256) e = launch_cluster_w8<8>(8, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+      else e = launch_cluster_w8<16>(16, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+    } else if (jv == 1) {
       if (NP == 256) e = launch_cluster_w<8>(8, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
       else e = launch_cluster_w<16>(16, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     } else if (NP == 256) e = launch_cluster<8, 4>(8, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);

@@ -365,6 +365,7 @@ def test_bad_arguments_are_rejected(L):
     lib = L.lib()
     assert lib.tnml_env_advance(None, None, None, None, 10, 4, 4, L.F64, None) == -1
     x = empty(4)
-    assert lib.tnml_feature_map(x.data_ptr(), x.data_ptr(), 2, 2, L.F32, None) == -2     # FP32 variant not built yet
+    # batch-independent entry points are FP64 only (tnml.h): the FP32/TF32 variant is refused there
+    assert lib.tnml_site_transpose(x.data_ptr(), x.data_ptr(), 1, 2, L.F32, None) == -2
     assert lib.tnml_feature_map(x.data_ptr(), x.data_ptr(), 2, 2, 7, None) == -1
     assert b"invalid" in lib.tnml_error_string(-1)
