@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
   // pass sees the flag, returns the identity rotation and the first-pass eigenvalues.
   // Export mode (Wout != nullptr): only the load + Cholesky preconditioning run here; the factor goes to global
   // memory for the cluster kernel.
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) {
-    if (!Wout) {
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) {
+    if (!Wout && pass_id == 2) {
       for (int e = threadIdx.x; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
       for (int e = threadIdx.x; e < n; e += blockDim.x) lam[e] = lam_prev[e];
       if (threadIdx.x == 0 && info) info[0] = 0.0;
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(E == 16 ? 256 : 128) k_jacobi_cluster(double* 
                                                         double* __restrict__ info, const double* __restrict__ skip_flag,
                                                         int pass_id, const int* __restrict__ sub) {
   constexpr int NP = 32 * E, NBmax = NP / K;
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
   // active problem size: the whole padded matrix, or (second pass on the small block) the first sub[0] rows
   int NB = NBmax;
   if (sub) {
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w(double* __restrict__ W
                                                           int pass_id, const int* __restrict__ sub) {
   constexpr int NP = 32 * E, K = 4, NBmax = NP / K;
   extern __shared__ __align__(16) double sm[];   // per block pair: 8 rows x NP, then 8 norms
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
   int NB = NBmax;
   if (sub) {
     const int nact = sub[0];
@@ -747,9 +747,9 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w(double* __restrict__ W
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Cluster version 3: blocks of EIGHT rows, one CTA-resident group of 8 warps per block pair, one rotation per warp.
-// Compared with version 2 (blocks of 4) a sweep has the same n - 1 sequential rotation sets but half the block-rounds,
-// i.e. half the L2 round trips (write back, cluster barrier, reload ~ 1900 cycles) that separate them.
+// Cluster version 3: blocks of K = 8 or 16 rows, one CTA-resident group of K warps per block pair, one rotation per
+// warp.  Compared with version 2 (blocks of 4) a sweep has the same n - 1 sequential rotation sets but 1/2 (1/4) of the
+// block-rounds, i.e. of the L2 round trips (write back, cluster barrier, reload ~ 1900 cycles) that separate them.
 // Mixed-precision inner products: while the previous sweep still saw a pair with a relative inner product above 1e-2
 // the rotation angle only has to be roughly right, so the dot product is accumulated and butterfly-reduced in FP32
 // (4-cycle FMAs and one shuffle per stage instead of 36-cycle FP64 operations and two shuffles); the rotation itself
@@ -757,7 +757,9 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w(double* __restrict__ W
 // The last sweeps (quadratic convergence from 1e-2 down to eps) run entirely in FP64.
 // flags[sweep]: bit 0 = some pair was above 1e-8, bit 1 = some pair was above 1e-2.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pair_barrier256(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_barrier_n(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int E, bool FAST>
 __device__ __forceinline__ int rotate_pair2(double* __restrict__ rx, double* __restrict__ ry, double* __restrict__ nx,
@@ -824,17 +826,17 @@ __device__ __forceinline__ int rotate_pair2(double* __restrict__ rx, double* __r
     *nx = al - tg;
     *ny = be + tg;
   }
-  return (g2 > 1e-16 * ab ? 1 : 0) | (g2 > 1e-4 * ab ? 2 : 0);   // bit 0: above 1e-8, bit 1: above 1e-2
+  return (g2 > 1e-16 * ab ? 1 : 0) | (g2 > 2.5e-3 * ab ? 2 : 0);   // bit 0: above 1e-8, bit 1: above 5e-2
 }
 
-template <int E>
+template <int E, int K>
 __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ Wg, double* __restrict__ nrm2g,
                                                            int* __restrict__ flags, int max_sweeps, double tol,
                                                            double* __restrict__ info, const double* __restrict__ skip_flag,
                                                            int pass_id, const int* __restrict__ sub, int mixed) {
-  constexpr int NP = 32 * E, K = 8, NBmax = NP / K;
-  extern __shared__ __align__(16) double sm[];   // per block pair: 16 rows x NP, then 16 norms
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  constexpr int NP = 32 * E, NBmax = NP / K, KT = 32 * K;   // KT = threads of one block pair
+  extern __shared__ __align__(16) double sm[];   // per block pair: 2K rows x NP, then 2K norms
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
   int NB = NBmax;
   if (sub) {
     const int nact = sub[0];
@@ -846,13 +848,13 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
   const int TW = NB / 2;                                          // active block pairs per block-round
   cg::cluster_group cl = cg::this_cluster();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bpl = warp >> 3, w = warp & 7;                        // local block pair, role inside the pair
-  const int bpc = blockDim.x >> 8;                                // block pairs per CTA
+  const int bpl = warp / K, w = warp % K;                          // local block pair, role inside the pair
+  const int bpc = blockDim.x / KT;                                 // block pairs per CTA
   const int bp = (int)cl.block_rank() * bpc + bpl;                // global block pair index
   const int gwarp = (int)cl.block_rank() * (blockDim.x >> 5) + warp, nwarps = (int)cl.num_blocks() * (blockDim.x >> 5);
   const bool active = bp < TW;
-  double* rows = sm + (size_t)bpl * (16 * NP + 16);
-  double* nr = rows + 16 * NP;
+  double* rows = sm + (size_t)bpl * (2 * K * NP + 2 * K);
+  double* nr = rows + 2 * K * NP;
   const double tol2 = tol * tol;
   int ra = (bp == 0) ? 0 : bp - 1, rb = NB - 2 - bp;
   int sweeps_done = 0;
@@ -872,43 +874,43 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
       if (active) {
         const int bi = (bp == 0) ? 0 : 1 + ra;
         const int bj = 1 + rb;
-        // stage: warp w brings row w of each block (rows 0-7 = block bi, 8-15 = block bj)
+        // stage: warp w brings row w of each block (rows 0..K-1 = block bi, K..2K-1 = block bj)
         double* const ga_ = Wg + (size_t)(K * bi + w) * NP + lane;
         double* const gb_ = Wg + (size_t)(K * bj + w) * NP + lane;
 #pragma unroll
         for (int k = 0; k < E; ++k) {
           rows[w * NP + lane + 32 * k] = __ldcg(ga_ + 32 * k);
-          rows[(8 + w) * NP + lane + 32 * k] = __ldcg(gb_ + 32 * k);
+          rows[(K + w) * NP + lane + 32 * k] = __ldcg(gb_ + 32 * k);
         }
-        if (lane == 0) { nr[w] = __ldcg(nrm2g + K * bi + w); nr[8 + w] = __ldcg(nrm2g + K * bj + w); }
-        pair_barrier256(1 + bpl);
-        if (round == 0) {   // the 28 pairs inside each block, once per sweep: round-robin of 8 players, 7 sets
-          const int base = (w >> 2) * 8, j = w & 3;
+        if (lane == 0) { nr[w] = __ldcg(nrm2g + K * bi + w); nr[K + w] = __ldcg(nrm2g + K * bj + w); }
+        pair_barrier_n(1 + bpl, KT);
+        if (round == 0) {   // the K(K-1)/2 pairs inside each block, once per sweep: round-robin of K players, K-1 sets
+          const int base = (w / (K / 2)) * K, j = w % (K / 2);
 #pragma unroll 1
-          for (int s = 0; s < 7; ++s) {
+          for (int s = 0; s < K - 1; ++s) {
             int p, q;
-            if (j == 0) { p = 7; q = s; }
-            else { p = (s + j) % 7; q = (s - j + 7) % 7; }
+            if (j == 0) { p = K - 1; q = s; }
+            else { p = (s + j) % (K - 1); q = (s - j + K - 1) % (K - 1); }
             rotated |= fast ? rotate_pair2<E, true>(rows + (base + p) * NP, rows + (base + q) * NP, nr + base + p,
                                                     nr + base + q, tol2, lane)
                             : rotate_pair2<E, false>(rows + (base + p) * NP, rows + (base + q) * NP, nr + base + p,
                                                      nr + base + q, tol2, lane);
-            pair_barrier256(1 + bpl);
+            pair_barrier_n(1 + bpl, KT);
           }
         }
 #pragma unroll 1
-        for (int s = 0; s < 8; ++s) {   // the 64 pairs across the two blocks: warp w rotates (w, 8 + (w+s)%8)
-          const int q = 8 + ((w + s) & 7);
+        for (int s = 0; s < K; ++s) {   // the K*K pairs across the two blocks: warp w rotates (w, K + (w+s)%K)
+          const int q = K + ((w + s) % K);
           rotated |= fast ? rotate_pair2<E, true>(rows + w * NP, rows + q * NP, nr + w, nr + q, tol2, lane)
                           : rotate_pair2<E, false>(rows + w * NP, rows + q * NP, nr + w, nr + q, tol2, lane);
-          pair_barrier256(1 + bpl);
+          pair_barrier_n(1 + bpl, KT);
         }
 #pragma unroll
         for (int k = 0; k < E; ++k) {
           ga_[32 * k] = rows[w * NP + lane + 32 * k];
-          gb_[32 * k] = rows[(8 + w) * NP + lane + 32 * k];
+          gb_[32 * k] = rows[(K + w) * NP + lane + 32 * k];
         }
-        if (lane == 0) { nrm2g[K * bi + w] = nr[w]; nrm2g[K * bj + w] = nr[8 + w]; }
+        if (lane == 0) { nrm2g[K * bi + w] = nr[w]; nrm2g[K * bj + w] = nr[K + w]; }
         ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
         rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
       }
@@ -930,10 +932,11 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
 __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict__ Wg, int NP, int n, int use_chol,
                                                        int pass_id, double* __restrict__ Vt, double* __restrict__ lam,
                                                        double* __restrict__ skip_flag, const double* __restrict__ lam_prev,
-                                                       double* __restrict__ info, int* __restrict__ sub) {
+                                                       double* __restrict__ info, int* __restrict__ sub, int m_defer) {
   __shared__ double nrm[SVD_MAXN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) {
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) {
+    if (pass_id == 3) return;                        // deferred tail refinement not needed: leave everything alone
     for (int e = tid; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
     for (int e = tid; e < n; e += blockDim.x) lam[e] = lam_prev[e];
     if (tid == 0 && info) info[0] = 0.0;
@@ -943,7 +946,7 @@ __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict_
   // otherwise identity rotation; the first k0 eigenvalues are the first pass's.
   const int nfull = n;
   int k0 = 0;
-  if (pass_id == 2 && sub) {
+  if (pass_id >= 2 && sub) {
     n = sub[0];
     k0 = sub[1];
     for (int e = tid; e < nfull * nfull; e += blockDim.x) {
@@ -986,7 +989,13 @@ __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) {
-      *skip_flag = (cnt == 0) ? 1.0 : 0.0;
+      // Deferred tail (m_defer = number of singular triplets the caller keeps): when every kept singular value sits in
+      // the accurate leading block (k0 = n - cnt >= m), the factors do not need the second pass at all -- only the
+      // reported values of the discarded tail do -- so the second pass is skipped on this (critical) path and
+      // skip_flag[1] = 0 asks the tail call (pass 3, off the critical path) to run it.
+      const bool defer = m_defer > 0 && sub && cnt > 0 && (n - cnt) >= m_defer;
+      skip_flag[0] = (cnt == 0 || defer) ? 1.0 : 0.0;
+      skip_flag[1] = defer ? 0.0 : 1.0;
       if (sub) { sub[0] = cnt; sub[1] = n - cnt; }
     }
   }
@@ -998,7 +1007,7 @@ __global__ void __launch_bounds__(256) k_sum_partials(const double* __restrict__
                                                       double* __restrict__ Wg, int* __restrict__ flags,
                                                       const double* __restrict__ skip_flag, int pass_id,
                                                       const int* __restrict__ sub, int unpadded) {
-  if (pass_id == 2 && skip_flag && *skip_flag != 0.0) return;
+  if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;
   if (sub) {
     n = sub[0];
     if (unpadded) NP = n;
@@ -1027,7 +1036,7 @@ template <int E, int K>
 __global__ void k_jacobi_cluster(double*, double*, int*, int, double, double*, const double*, int, const int*);
 template <int E>
 __global__ void k_jacobi_cluster_w(double*, double*, int*, int, double, double*, const double*, int, const int*);
-template <int E>
+template <int E, int K>
 __global__ void k_jacobi_cluster_w8(double*, double*, int*, int, double, double*, const double*, int, const int*, int);
 
 static cudaError_t jacobi_prepare() {
@@ -1042,11 +1051,18 @@ static cudaError_t jacobi_prepare() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_jacobi_cluster_w<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (8 * 256 + 8) * 8);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16, 8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 512 + 16) * 8);
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_jacobi_cluster_w8<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 256 + 16) * 8);
+  // dynamic shared memory: (block pairs per CTA) x (2K rows x NP + 2K norms) doubles
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 512 + 16) * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (16 * 256 + 16) * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_jacobi_cluster_w8<16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 512 + 32) * 8);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_jacobi_cluster_w8<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (32 * 256 + 32) * 8);
 }
 
 template <int E, int K>
@@ -1086,14 +1102,17 @@ static cudaError_t launch_cluster_w(int ctas, int threads, double* Wg, double* n
   return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w<E>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub);
 }
 
-template <int E>
-static cudaError_t launch_cluster_w8(int ctas, int threads, double* Wg, double* nrm2g, int* flags, double tol,
-                                     double* info, const double* skip, int pass_id, const int* sub, int mixed,
-                                     cudaStream_t st) {
+// K rows per block; NP / (2K) block pairs of K warps each, spread over the CTAs of one cluster (512 threads per CTA at most)
+template <int E, int K>
+static cudaError_t launch_cluster_w8(double* Wg, double* nrm2g, int* flags, double tol, double* info, const double* skip,
+                                     int pass_id, const int* sub, int mixed, cudaStream_t st) {
+  constexpr int NP = 32 * E, pairs = NP / (2 * K), max_ctas = (E == 16) ? 16 : 8;   // 16: non-portable cluster size
+  constexpr int ctas = pairs < max_ctas ? pairs : max_ctas, per_cta = pairs / ctas, threads = per_cta * 32 * K;
+  static_assert(threads <= 512 && per_cta * ctas == pairs, "cluster shape");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = (size_t)(threads / 256) * (16 * 32 * E + 16) * sizeof(double);
+  cfg.dynamicSmemBytes = (size_t)per_cta * (2 * K * NP + 2 * K) * sizeof(double);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1103,8 +1122,17 @@ static cudaError_t launch_cluster_w8(int ctas, int threads, double* Wg, double* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int max_sweeps = 60;
-  return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w8<E>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub,
+  return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w8<E, K>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub,
                             mixed);
+}
+
+static int jacobi_block_rows() {   // TNML_JACOBI_BLOCK = 8 (default) or 16 rows per block
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_JACOBI_BLOCK");
+    v = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  return v;
 }
 
 // TNML_JACOBI_VARIANT: 2 = blocks of 8 rows, FP64 inner products (default); 3 = same + FP32 inner products in the early
@@ -1131,7 +1159,7 @@ struct JacobiBuffers {
 // (the small singular values) is decomposed -- the partials then hold that block's Gram matrix.
 static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
                          int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
-                         cudaStream_t st) {
+                         cudaStream_t st, int m_defer = 0) {
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) {
     TNML_COUNT(1);
@@ -1146,7 +1174,7 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
                                                 lam_prev, nullptr, nullptr, nullptr);
     return tnml_launch_status();
   }
-  const int* sub2 = (pass_id == 2) ? sub : nullptr;   // sub-block mode of the second pass
+  const int* sub2 = (pass_id >= 2) ? sub : nullptr;   // sub-block mode of the second pass
   cudaError_t e;
   int NP;
   TNML_COUNT(3);
@@ -1165,7 +1193,9 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
                                                               sub2, 0);
     }
     const int jv = jacobi_variant();
-    if (jv >= 2) e = launch_cluster_w8<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+    if (jv >= 2 && jacobi_block_rows() == 16)
+      e = launch_cluster_w8<4, 16>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+    else if (jv >= 2) e = launch_cluster_w8<4, 8>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
     else if (jv == 1) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     else e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   } else {
@@ -1175,8 +1205,11 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
                                                             0);
     const int jv = jacobi_variant();
     if (jv >= 2) {
-      if (NP == 256) e = launch_cluster_w8<8>(8, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
-      else e = launch_cluster_w8<16>(16, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+      const bool k16 = jacobi_block_rows() == 16;
+      if (NP == 256 && k16) e = launch_cluster_w8<8, 16>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+      else if (NP == 256) e = launch_cluster_w8<8, 8>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+      else if (k16) e = launch_cluster_w8<16, 16>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+      else e = launch_cluster_w8<16, 8>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
     } else if (jv == 1) {
       if (NP == 256) e = launch_cluster_w<8>(8, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
       else e = launch_cluster_w<16>(16, 512, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
@@ -1184,7 +1217,7 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
     else e = launch_cluster<16, 2>(16, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   }
   if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-  k_jacobi_finish<<<1, 512, 0, st>>>(jb.Wg, NP, n, use_chol, pass_id, Vt, lam, skip, lam_prev, info, sub);
+  k_jacobi_finish<<<1, 512, 0, st>>>(jb.Wg, NP, n, use_chol, pass_id, Vt, lam, skip, lam_prev, info, sub, m_defer);
   return tnml_launch_status();
 }
 
@@ -1275,7 +1308,7 @@ static SvdPlan svd_plan_rc(int R, int C) {
   p.off_lam1 = o; o += p.n;
   p.off_lam2 = o; o += p.n;
   p.off_Y = o; o += (size_t)p.n * p.Nl;
-  p.off_skip = o; o += 1;
+  p.off_skip = o; o += 2;      // [0] second pass skipped on the critical path, [1] deferred tail pass skipped
   p.off_Wg = o; o += (size_t)p.NP * p.NP;
   p.off_nrm = o; o += p.NP;
   p.off_flags = o; o += 32;   // 64 ints
@@ -1310,15 +1343,17 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
   const int tiles = tnml_cdiv(n, GRAM_TILE);
   const dim3 ggrid(p.nparts, tiles, tiles);
+  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+  const int m_defer = (refine == 3 && cluster) ? m : 0;     // refine 3 = refine 1 + deferred tail (svd_tail)
+  if (refine == 3) refine = 1;
   double* skip1 = refine == 1 ? skip : nullptr;
   // refine == 1 on the cluster path: the second pass only decomposes the block of small singular values
-  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   int* sub = (refine == 1 && cluster) ? (int*)(w + p.off_sub) : nullptr;
   int rc;
 
   TNML_COUNT(1);
   k_gram<<<ggrid, 256, 0, st>>>(X, ss, sl, n, Nl, p.lc, partial, nullptr, nullptr);
-  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st);
+  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer);
   if (rc) return rc;
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
@@ -1340,6 +1375,34 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   return tnml_launch_status();
 }
 
+
+// Deferred refinement of the discarded tail's singular VALUES (see k_jacobi_finish): the second pass on the block of
+// small singular values, run off the critical path after a refine = 3 split; every kernel returns at once unless the
+// split set skip[1] = 0.  Only svals (the tail entries and the pass-2 sweep counter) are written.
+__global__ void __launch_bounds__(256) k_tail_svals(const double* __restrict__ lam2, const int* __restrict__ sub,
+                                                    const double* __restrict__ skip2, int n, double* __restrict__ svals) {
+  if (*skip2 != 0.0) return;
+  const int k0 = sub[1];
+  for (int k = k0 + threadIdx.x; k < n; k += 256) svals[k] = sqrt(lam2[k]);
+}
+
+static int svd_tail(SvdPlan p, double* svals, double* w, cudaStream_t st) {
+  const int n = p.n, Nl = p.Nl;
+  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+  if (!cluster) return TNML_OK;                       // refine 3 never defers on the single-CTA path
+  double *partial = w + p.off_partial, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1, *lam2 = w + p.off_lam2,
+         *Y = w + p.off_Y, *skip2 = w + p.off_skip + 1;
+  JacobiBuffers jb{w + p.off_Wg, w + p.off_nrm, (int*)(w + p.off_flags), Y};
+  int* sub = (int*)(w + p.off_sub);
+  const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
+  const int tiles = tnml_cdiv(n, GRAM_TILE);
+  TNML_COUNT(2);
+  k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
+  int rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 1, 3, svals + n + 1, skip2, lam1, jb, sub, st);
+  if (rc) return rc;
+  k_tail_svals<<<1, 256, 0, st>>>(lam2, sub, skip2, n, svals);
+  return tnml_launch_status();
+}
 }  // namespace tnml
 
 using namespace tnml;
@@ -1381,4 +1444,11 @@ extern "C" int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* 
   const Idx3 colmap{1, 1, 1, 0, 0};              // SVh[k][j]
   return svd_core((const double*)Mx, p, m, refine, (double*)US, rowmap, 1, (double*)SVh, colmap, C, (double*)svals,
                   (double*)ws, (cudaStream_t)stream);
+}
+
+extern "C" int tnml_svd_split_tail(void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir, int32_t dtype,
+                                   tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(svals && ws && Dl > 0 && Dr > 0 && L > 0);
+  return svd_tail(svd_plan(Dl, Dr, L, left_dir), (double*)svals, (double*)ws, (cudaStream_t)stream);
 }

@@ -119,6 +119,12 @@ class SweepEngine:
         self.project_ctas = 110       # grid cap of the projection while the SVD runs beside it (0 = no cap)
         self._side = None
         self._inflight = None
+        # the second Jacobi pass that only refines the reported singular values of the DISCARDED tail runs on a third,
+        # normal-priority stream after the split (tnml_svd_split refine = 3 + tnml_svd_split_tail); two workspaces
+        # alternate so that the next split does not wait for it
+        self.defer_tail = True
+        self._tail = None
+        self._tail_evt = [None, None]
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -132,6 +138,16 @@ class SweepEngine:
         if self._side is None:
             self._side = torch.cuda.Stream(device=self.device, priority=-1)   # the SVD is on the critical path
         return self._side
+
+    def _tail_stream(self):
+        if self._tail is None:
+            self._tail = torch.cuda.Stream(device=self.device)
+        return self._tail
+
+    def _join_tail(self):
+        """Order the current stream after every deferred tail refinement enqueued so far."""
+        if self._tail is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._tail)
 
     def _empty(self, n):
         return torch.empty(int(n), dtype=torch.float64, device=self.device)
@@ -349,6 +365,13 @@ class SweepEngine:
         S = self.S
         self.set_labels(y)
         nsteps = S - 1 if nsteps is None else nsteps
+        self._join_tail()                             # the previous record may still receive tail singular values
+        # both SVD workspaces at their largest size of the chain up front: they are read by the tail stream, so they must
+        # not be re-allocated in the middle of a sweep
+        cap = self._dcap()
+        nb = max(_lib.lib().tnml_svd_split_workspace_bytes(cap, cap, self.L, d) for d in (0, 1))
+        self._workspace("svd0", nb)
+        self._workspace("svd1", nb)
         self._label_to("L" if left_dir else "R")
         if L2_flag:
             self._build_norm_stack(left_dir)
@@ -440,22 +463,38 @@ class SweepEngine:
         m = self._choose_m(left_dir, Dl, R, Cc)
         new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
         new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
-        ws_svd = self._workspace("svd", _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
+        defer = bool(self.defer_tail and self.svd_refine == 1 and side is not main)
+        par = step & 1
+        ws_svd = self._workspace("svd%d" % par, _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
         f_out = self.f_buf[1 - self.f_cur]
         ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
         if side is not main:
             side.wait_stream(main)                      # B' is ready
+        sv_ptr = self.hist["svals"].data_ptr() + step * self.hist["svals"].shape[1] * 8
+        ldir = 1 if left_dir else 0
         # the SVD is issued first: its kernels are short or small and should get SMs before the projection fills the GPU
         with torch.cuda.stream(side):
+            if self._tail_evt[par] is not None:
+                side.wait_event(self._tail_evt[par])    # this workspace's previous tail refinement has finished
             with _Timed(self, "svd_split", 0.0):
-                call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), self.hist["svals"].data_ptr() +
-                     step * self.hist["svals"].shape[1] * 8, _ptr(ws_svd), Dl, Dr, L, m, 1 if left_dir else 0,
-                     self.svd_refine, F64, side.cuda_stream)
+                call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
+                     3 if defer else self.svd_refine, F64, side.cuda_stream)
+            if defer:
+                split_done = torch.cuda.Event()
+                split_done.record(side)
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
             # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
                  Dl, Dr, L, cap, self.DT, st)
+        if defer:
+            tail = self._tail_stream()
+            tail.wait_event(split_done)
+            with torch.cuda.stream(tail):
+                call("tnml_svd_split_tail", sv_ptr, _ptr(ws_svd), Dl, Dr, L, ldir, F64, tail.cuda_stream)
+                evt = torch.cuda.Event()
+                evt.record(tail)
+            self._tail_evt[par] = evt
         self.f_cur = 1 - self.f_cur
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
@@ -478,6 +517,7 @@ class SweepEngine:
     def history(self):
         """Fetch the per-step record of the last sweep (one device->host copy)."""
         n = self.hist["n"]
+        self._join_tail()
         met = self.hist["metrics"][:n].cpu().numpy()
         stats = self.hist["stats"][:n].cpu().numpy()
         sv = self.hist["svals"][:n].cpu().numpy()
