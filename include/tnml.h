@@ -157,14 +157,14 @@ int tnml_norm_env_step(const void* Ein, const void* site, void* Eout, void* ws, 
  * first pass finds sigma_min/sigma_max > 3e-4 (then it is provably unnecessary at the 1e-11 level); 2 = always;
  * 3 = like 1, but when all m kept singular values lie in the accurate leading block the second pass -- which then
  * only improves the REPORTED values of the discarded tail, not the factors -- is left to tnml_svd_split_tail, which the
- * caller enqueues later on any stream ordered after this call (off the critical path of the sweep).  The workspace
- * must stay untouched until that call has run; svals is complete only after it. */
+ * caller enqueues later on any stream ordered after this call (off the critical path of the sweep).  Bnew and the
+ * workspace must stay untouched until that call has run; svals is complete only after it. */
 int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
 int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
                    int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream);
 
-int tnml_svd_split_tail(void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir, int32_t dtype,
-                        tnml_stream_t stream);
+int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir,
+                        int32_t dtype, tnml_stream_t stream);
 
 /* General form for Network.tensor_svd on any 2-D Tensor (NC:839-962): Mx [R][C] -> US [R][m] = U sqrt(S),
  * SVh [m][C] = sqrt(S) Vh; svals as above (min(R,C) + 2 values). */

@@ -253,15 +253,18 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     // per-warp pivot candidates: largest remaining diagonal entry (ties -> smallest index); every thread then
     // reduces the NWG candidates itself, so the selection needs no barrier of its own
     auto warp_candidate = [&]() {                        // warps of group 0 only
-      double best = active[j] ? diag[j] : -1.0;
+      // the butterfly compares single-precision keys (one shuffle per stage instead of two): diagonal entries that
+      // agree to 2^-24 are interchangeable as pivots; ties go to the smaller index, so the choice stays deterministic
+      const double mine = active[j] ? diag[j] : -1.0;
+      float best = (float)mine;
       int bi = active[j] ? j : -1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
       }
-      if (lane == 0) { cand_v[warp] = best; cand_i[warp] = bi; }
+      if (lane == 0) { cand_v[warp] = bi >= 0 ? diag[bi] : -1.0; cand_i[warp] = bi; }
     };
     auto pick = [&](double& best, int& bi) {
       best = -1.0; bi = -1;
@@ -302,7 +305,19 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
 #pragma unroll
         for (int g = 0; g < NG; ++g) { scc -= part[g][c]; sj -= part[g][j]; }
         scc = fmax(scc, piv_floor);
-        const double inv = rsqrt(scc);                   // one reciprocal square root instead of sqrt + division
+        // reciprocal square root: MUFU.RSQ seed on the power-of-two-normalised value + one third-order correction
+        // (error ~ e^3, e ~ 2^-22) -- the library rsqrt() is a ~20-deep chain of dependent FP64 operations, and this
+        // sits on the critical path of every elimination step
+        double inv;
+        {
+          const int ex2 = ((__double2hiint(scc) >> 20) & 0x7ff) - 1023;          // scc = f * 2^ex2, f in [1, 2)
+          const int hx = ex2 >> 1;                                               // floor(ex2 / 2)
+          const double xs = scc * __hiloint2double((1023 - 2 * hx) << 20, 0);    // in [1, 4)
+          const double y0 = (double)rsqrt_approx((float)xs);
+          const double e = fma(-xs * y0, y0, 1.0);
+          const double y1 = fma(y0 * e, fma(e, 0.375, 0.5), y0);
+          inv = y1 * __hiloint2double((1023 - hx) << 20, 0);
+        }
         double r = 0.0;
         if (j == c) r = scc * inv;
         else if (active[j]) { r = sj * inv; diag[j] = fma(-r, r, diag[j]); }
@@ -937,8 +952,7 @@ __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
   if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) {
     if (pass_id == 3) return;                        // deferred tail refinement not needed: leave everything alone
-    for (int e = tid; e < n * n; e += blockDim.x) Vt[e] = (e / n == e % n) ? 1.0 : 0.0;
-    for (int e = tid; e < n; e += blockDim.x) lam[e] = lam_prev[e];
+    // (the factor kernels read the skip flag themselves and fall back to the first pass's rotation and eigenvalues)
     if (tid == 0 && info) info[0] = 0.0;
     return;
   }
@@ -1224,11 +1238,29 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
 // Out[k][l] = scale_k * sum_s Vt[k][s] In(s,l), k < kmax; scale_k = lam_k^(-1/4) if lam != nullptr else 1
 // written at out + k*kstride + map(l).  grid = (ceil(Nl/32), ceil(kmax/32)), 256 threads; s in chunks of 128.
 constexpr int ROWS_SC = 64;
+// flag (device, optional): run_if < 0 -> plain kernel; run_if = 0 / 1 -> return unless (*flag != 0) == run_if;
+// run_if = 2 -> when *flag != 0 use the alternative operands (Xa, ssa, sla, Vta, lama) instead (second pass skipped).
+struct RowsAlt {
+  const double* flag;
+  int run_if;
+  const double* Xa;
+  long long ssa, sla;
+  const double* Vta;
+  const double* lama;
+};
 __global__ void __launch_bounds__(256) k_rows(const double* __restrict__ X, long long ss, long long sl, int n, int Nl,
                                               const double* __restrict__ Vt, const double* __restrict__ lam, int kmax,
-                                              double* __restrict__ out, long long kstride, Idx3 map) {
+                                              double* __restrict__ out, long long kstride, Idx3 map, RowsAlt alt) {
   __shared__ double Vs[32][ROWS_SC + 1];
   __shared__ double Is[ROWS_SC][33];
+  if (alt.run_if >= 0) {
+    const bool set = *alt.flag != 0.0;
+    if (alt.run_if <= 1) {
+      if ((int)set != alt.run_if) return;
+    } else if (set) {
+      X = alt.Xa; ss = alt.ssa; sl = alt.sla; Vt = alt.Vta; lam = alt.lama;
+    }
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int l0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1266,10 +1298,13 @@ __global__ void __launch_bounds__(256) k_rows(const double* __restrict__ X, long
 
 // Fs[s][k] = lam_k^(1/4) * sum_t Vt1[t][s] * Vt2[k][t]   (U = U1 U2); Vt2 == nullptr -> U = U1.
 // Also emits the singular values sqrt(lam).
+// skipf (device, optional): when *skipf != 0 the second pass did not run: U = U1 and lam = lam_alt.
 __global__ void __launch_bounds__(256) k_short(const double* __restrict__ Vt1, const double* __restrict__ Vt2,
                                                const double* __restrict__ lam, int n, int m, double* __restrict__ out,
-                                               long long kstride, Idx3 map, double* __restrict__ svals) {
+                                               long long kstride, Idx3 map, double* __restrict__ svals,
+                                               const double* __restrict__ skipf, const double* __restrict__ lam_alt) {
   int idx = blockIdx.x * 256 + threadIdx.x;
+  if (skipf && *skipf != 0.0) { Vt2 = nullptr; lam = lam_alt; }
   if (idx < n) svals[idx] = sqrt(lam[idx]);
   if (idx >= n * m) return;
   const int s = idx % n, k = idx / n;
@@ -1358,19 +1393,28 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
     TNML_COUNT(4);
-    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense);
+    const RowsAlt none{nullptr, -1, nullptr, 0, 0, nullptr, nullptr};
+    // Y is only needed when the second pass runs on this path (skip1 == nullptr: always)
+    const RowsAlt only_if_pass2{skip1, skip1 ? 0 : -1, nullptr, 0, 0, nullptr, nullptr};
+    const RowsAlt first_pass_if_skipped{skip1, skip1 ? 2 : -1, X, ss, sl, vt1, lam1};
+    k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense,
+                                                                    only_if_pass2);
+    (void)none;
     k_gram<<<ggrid, 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip1, sub);
     rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, sub ? 1 : 0, 2, svals + n + 1, skip1, lam1, jb, sub,
                        st);
     if (rc) return rc;
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, 0, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
-                                                                    k_long_stride, map_long);
-    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short, svals);
+                                                                    k_long_stride, map_long, first_pass_if_skipped);
+    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, vt2, lam2, n, m, dst_short, k_short_stride, map_short, svals,
+                                                   skip1, lam1);
   } else {
     TNML_COUNT(2);
+    const RowsAlt none{nullptr, -1, nullptr, 0, 0, nullptr, nullptr};
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, lam1, m, dst_long,
-                                                                    k_long_stride, map_long);
-    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short, svals);
+                                                                    k_long_stride, map_long, none);
+    k_short<<<tnml_cdiv(n * m, 256), 256, 0, st>>>(vt1, nullptr, lam1, n, m, dst_short, k_short_stride, map_short, svals,
+                                                   nullptr, nullptr);
   }
   return tnml_launch_status();
 }
@@ -1386,7 +1430,7 @@ __global__ void __launch_bounds__(256) k_tail_svals(const double* __restrict__ l
   for (int k = k0 + threadIdx.x; k < n; k += 256) svals[k] = sqrt(lam2[k]);
 }
 
-static int svd_tail(SvdPlan p, double* svals, double* w, cudaStream_t st) {
+static int svd_tail(const double* X, SvdPlan p, double* svals, double* w, cudaStream_t st) {
   const int n = p.n, Nl = p.Nl;
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) return TNML_OK;                       // refine 3 never defers on the single-CTA path
@@ -1396,7 +1440,12 @@ static int svd_tail(SvdPlan p, double* svals, double* w, cudaStream_t st) {
   int* sub = (int*)(w + p.off_sub);
   const double tol_final = sqrt((double)n) * 2.220446049250313e-16;
   const int tiles = tnml_cdiv(n, GRAM_TILE);
-  TNML_COUNT(2);
+  const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
+  const Idx3 dense{1, 1, 1, 0, 0};
+  const RowsAlt if_deferred{skip2, 0, nullptr, 0, 0, nullptr, nullptr};
+  TNML_COUNT(3);
+  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, w + p.off_vt1, nullptr, n, Y, Nl,
+                                                                  dense, if_deferred);
   k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
   int rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 1, 3, svals + n + 1, skip2, lam1, jb, sub, st);
   if (rc) return rc;
@@ -1446,9 +1495,9 @@ extern "C" int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* 
                   (double*)ws, (cudaStream_t)stream);
 }
 
-extern "C" int tnml_svd_split_tail(void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir, int32_t dtype,
-                                   tnml_stream_t stream) {
+extern "C" int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L,
+                                   int32_t left_dir, int32_t dtype, tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
-  TNML_REQUIRE(svals && ws && Dl > 0 && Dr > 0 && L > 0);
-  return svd_tail(svd_plan(Dl, Dr, L, left_dir), (double*)svals, (double*)ws, (cudaStream_t)stream);
+  TNML_REQUIRE(Bnew && svals && ws && Dl > 0 && Dr > 0 && L > 0);
+  return svd_tail((const double*)Bnew, svd_plan(Dl, Dr, L, left_dir), (double*)svals, (double*)ws, (cudaStream_t)stream);
 }

@@ -12,6 +12,8 @@ Index conventions:
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -116,7 +118,8 @@ class SweepEngine:
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
-        self.project_ctas = 110       # grid cap of the projection while the SVD runs beside it (0 = no cap)
+        self.project_ctas = int(os.environ.get("TNML_PROJECT_CTAS", "120"))   # grid cap of the projection while the SVD
+                                                                          # split runs beside it (0 = no cap)
         self._side = None
         self._inflight = None
         # the second Jacobi pass that only refines the reported singular values of the DISCARDED tail runs on a third,
@@ -491,7 +494,8 @@ class SweepEngine:
             tail = self._tail_stream()
             tail.wait_event(split_done)
             with torch.cuda.stream(tail):
-                call("tnml_svd_split_tail", sv_ptr, _ptr(ws_svd), Dl, Dr, L, ldir, F64, tail.cuda_stream)
+                Bn.record_stream(tail)                  # B' is read again by the tail refinement
+                call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), Dl, Dr, L, ldir, F64, tail.cuda_stream)
                 evt = torch.cuda.Event()
                 evt.record(tail)
             self._tail_evt[par] = evt
