@@ -479,6 +479,121 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Pivoted Cholesky preconditioning for 128 < n <= 512 (bond dimension 128 / 256): the same left-looking algorithm as
+// in k_jacobi, in place on the padded NP x NP Gram matrix in GLOBAL memory (L2-resident), one CTA of 1024 threads.
+// The first CAP factor rows -- the ones every later step reads -- are also kept in shared memory.
+// Without it the cluster sweeps work on sigma^2 and need ~26 sweeps at n = 256; with it 8-10.
+// ---------------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(1024, 1) k_chol_big(double* __restrict__ Wg, int n, int cap_rows,
+                                                      int* __restrict__ flags_out) {
+  constexpr int NT = 1024, NG = NT / NP, NWG = NP / 32;
+  extern __shared__ __align__(16) double cache[];        // cap_rows x NP: factor rows 0 .. cap_rows-1 in pivot order
+  __shared__ double part[NG][NP], diag[NP];
+  __shared__ unsigned char active[NP];
+  __shared__ int piv[NP];
+  __shared__ double cand_v[NWG];
+  __shared__ int cand_i[NWG];
+  __shared__ double piv_floor_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int j = tid % NP, gq = tid / NP;
+  for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
+  for (int jj = tid; jj < NP; jj += NT) { active[jj] = jj < n; diag[jj] = jj < n ? Wg[(size_t)jj * NP + jj] : 0.0; }
+  __syncthreads();
+  auto warp_candidate = [&]() {                          // warps of group 0 only (they own the columns)
+    const double mine = active[j] ? diag[j] : -1.0;
+    float best = (float)mine;
+    int bi = active[j] ? j : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { cand_v[warp] = bi >= 0 ? diag[bi] : -1.0; cand_i[warp] = bi; }
+  };
+  auto pick = [&](double& best, int& bi) {
+    best = -1.0; bi = -1;
+#pragma unroll
+    for (int c = 0; c < NWG; ++c) {
+      const double v = cand_v[c];
+      const int i = cand_i[c];
+      if (i >= 0 && (bi < 0 || v > best)) { best = v; bi = i; }
+    }
+  };
+  if (gq == 0) warp_candidate();
+  __syncthreads();
+  double pbest; int c;
+  pick(pbest, c);
+  const double piv_floor = pbest * (double)n * 2.220446049250313e-16;
+  if (tid == 0) piv_floor_s = piv_floor;
+  for (int k = 0; k < n; ++k) {
+    if (c < 0 || !(pbest > piv_floor)) break;            // numerically rank deficient from here on (uniform)
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const int kc = min(k, cap_rows);
+    int m = gq;
+    for (; m + 3 * NG < kc; m += 4 * NG) {                // rows cached in shared memory
+      const double *r0 = cache + (size_t)m * NP, *r1 = r0 + (size_t)NG * NP, *r2 = r1 + (size_t)NG * NP,
+                   *r3 = r2 + (size_t)NG * NP;
+      acc0 = fma(r0[c], r0[j], acc0);
+      acc1 = fma(r1[c], r1[j], acc1);
+      acc2 = fma(r2[c], r2[j], acc2);
+      acc3 = fma(r3[c], r3[j], acc3);
+    }
+    for (; m < kc; m += NG) {
+      const double* r0 = cache + (size_t)m * NP;
+      acc0 = fma(r0[c], r0[j], acc0);
+    }
+    // m is now the first row >= kc of this group's stride (m == gq (mod NG)): the remaining rows live in global memory
+    for (; m + 3 * NG < k; m += 4 * NG) {
+      const double *r0 = Wg + (size_t)piv[m] * NP, *r1 = Wg + (size_t)piv[m + NG] * NP,
+                   *r2 = Wg + (size_t)piv[m + 2 * NG] * NP, *r3 = Wg + (size_t)piv[m + 3 * NG] * NP;
+      acc0 = fma(r0[c], r0[j], acc0);
+      acc1 = fma(r1[c], r1[j], acc1);
+      acc2 = fma(r2[c], r2[j], acc2);
+      acc3 = fma(r3[c], r3[j], acc3);
+    }
+    for (; m < k; m += NG) {
+      const double* r0 = Wg + (size_t)piv[m] * NP;
+      acc0 = fma(r0[c], r0[j], acc0);
+    }
+    part[gq][j] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (gq == 0) {
+      double scc = Wg[(size_t)c * NP + c], sj = Wg[(size_t)c * NP + j];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) { scc -= part[g][c]; sj -= part[g][j]; }
+      scc = fmax(scc, piv_floor);
+      double inv;
+      {
+        const int ex2 = ((__double2hiint(scc) >> 20) & 0x7ff) - 1023;
+        const int hx = ex2 >> 1;
+        const double xs = scc * __hiloint2double((1023 - 2 * hx) << 20, 0);
+        const double y0 = (double)rsqrt_approx((float)xs);
+        const double e = fma(-xs * y0, y0, 1.0);
+        const double y1 = fma(y0 * e, fma(e, 0.375, 0.5), y0);
+        inv = y1 * __hiloint2double((1023 - hx) << 20, 0);
+      }
+      double r = 0.0;
+      if (j == c) r = scc * inv;
+      else if (active[j]) { r = sj * inv; diag[j] = fma(-r, r, diag[j]); }
+      Wg[(size_t)c * NP + j] = r;
+      if (k < cap_rows) cache[(size_t)k * NP + j] = r;
+      if (j == c) { active[c] = 0; piv[k] = c; }
+      __syncwarp();
+      warp_candidate();
+    }
+    __syncthreads();
+    pick(pbest, c);
+  }
+  // rows never eliminated (numerical rank deficiency): tiny multiples of the unit vectors complete the basis
+  __syncthreads();
+  const double tiny = sqrt(piv_floor_s);
+  for (int e = tid; e < NP * NP; e += NT)
+    if (active[e / NP]) Wg[e] = (e / NP == e % NP) ? tiny : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Cluster version: the same block-Jacobi ordering with the matrix in global memory (L2-resident) and the block
 // pairs of a block-round spread over the CTAs of ONE thread-block cluster; a cluster barrier (release / acquire at
 // cluster scope, which also orders the global-memory traffic) separates the block-rounds.  Two uses:
@@ -1053,8 +1168,14 @@ __global__ void k_jacobi_cluster_w(double*, double*, int*, int, double, double*,
 template <int E, int K>
 __global__ void k_jacobi_cluster_w8(double*, double*, int*, int, double, double*, const double*, int, const int*, int);
 
+constexpr int CHOL_BIG_CAP_256 = 100, CHOL_BIG_CAP_512 = 50;   // factor rows cached in shared memory (~200 KB)
+
 static cudaError_t jacobi_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_chol_big<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_BIG_CAP_256 * 256 * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_chol_big<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_BIG_CAP_512 * 512 * 8);
   if (e != cudaSuccess) return e;
   // n = 512 uses a cluster of 16 CTAs (above the portable limit of 8)
   e = cudaFuncSetAttribute(k_jacobi_cluster<16, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -1140,6 +1261,15 @@ static cudaError_t launch_cluster_w8(double* Wg, double* nrm2g, int* flags, doub
                             mixed);
 }
 
+static int chol_big_enabled() {   // TNML_CHOL_BIG=0: no Cholesky preconditioning for n > 128 (A/B knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_CHOL_BIG");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
 static int jacobi_block_rows() {   // TNML_JACOBI_BLOCK = 8 (default) or 16 rows per block
   static int v = -1;
   if (v < 0) {
@@ -1213,10 +1343,18 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
     else if (jv == 1) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     else e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   } else {
-    use_chol = 0;
     NP = n <= 256 ? 256 : 512;
     k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id, sub2,
                                                             0);
+    // first pass: pivoted Cholesky preconditioning in global memory (TNML_CHOL_BIG=0 switches it off); the second pass
+    // on the small block keeps the plain Gram form
+    if (use_chol && pass_id == 1 && chol_big_enabled()) {
+      TNML_COUNT(1);
+      if (NP == 256) k_chol_big<256><<<1, 1024, CHOL_BIG_CAP_256 * 256 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_256, jb.flags);
+      else k_chol_big<512><<<1, 1024, CHOL_BIG_CAP_512 * 512 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_512, jb.flags);
+    } else {
+      use_chol = 0;
+    }
     const int jv = jacobi_variant();
     if (jv >= 2) {
       const bool k16 = jacobi_block_rows() == 16;

@@ -494,7 +494,11 @@ class SweepEngine:
             tail = self._tail_stream()
             tail.wait_event(split_done)
             with torch.cuda.stream(tail):
-                Bn.record_stream(tail)                  # B' is read again by the tail refinement
+                # these three are used by the tail stream after the main stream is done with them: tell the allocator, so
+                # that dropping the engine (or re-sizing a workspace) cannot hand their memory out while a tail is pending
+                Bn.record_stream(tail)
+                ws_svd.record_stream(tail)
+                self.hist["svals"].record_stream(tail)
                 call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), Dl, Dr, L, ldir, F64, tail.cuda_stream)
                 evt = torch.cuda.Event()
                 evt.record(tail)
