@@ -242,15 +242,20 @@ def test_norm_env_step(L, Dl, Dr):
     assert rel(out, O.norm_env_left_step(ER, A)) < TOL
 
 
-def _run_svd(L, B, left_dir, m, refine=2):
+def _run_svd(L, B, left_dir, m, refine=2, tail=False, before_tail=None):
     Dl, _, nl, _, Dr = B.shape
     site_p = empty(Dl * 2 * m * (nl if left_dir else 1))
     site_q = empty(m * 2 * Dr * (1 if left_dir else nl))
     sv = torch.full((4 * max(Dl, Dr, nl) * 2,), float("nan"), dtype=torch.float64, device="cuda")
     ws = ws_for(L, "tnml_svd_split_workspace_bytes", Dl, Dr, nl, left_dir)
-    L.call("tnml_svd_split", dev(B).data_ptr(), site_p.data_ptr(), site_q.data_ptr(), sv.data_ptr(), ws.data_ptr(), Dl,
+    Bd = dev(B)
+    L.call("tnml_svd_split", Bd.data_ptr(), site_p.data_ptr(), site_q.data_ptr(), sv.data_ptr(), ws.data_ptr(), Dl,
            Dr, nl, m, left_dir, refine, L.F64, st())
     n = min(2 * Dl * (nl if left_dir else 1), 2 * Dr * (1 if left_dir else nl))
+    if tail:          # refine = 3: the deferred refinement of the discarded tail's singular values
+        if before_tail is not None:
+            before_tail.append((sv.cpu().numpy()[:n].copy(), site_p.cpu().numpy().copy(), site_q.cpu().numpy().copy()))
+        L.call("tnml_svd_split_tail", Bd.data_ptr(), sv.data_ptr(), ws.data_ptr(), Dl, Dr, nl, left_dir, L.F64, st())
     sp, sq = site_p.cpu().numpy(), site_q.cpu().numpy()
     if not left_dir:
         Ap, Aq = sp.reshape(Dl, 2, m), sq.reshape(m, 2, nl, Dr)
@@ -313,11 +318,23 @@ def test_svd_two_scale_spectrum_small_block_refinement(L, Dl, Dr, nl, left_dir):
     Mx = (Q1 * S) @ Q2.T
     B = Mx.reshape(Dl, 2, nl, 2, Dr)
     m = n // 2
+    want = ((Q1[:, :m] * S[:m]) @ Q2[:, :m].T).reshape(B.shape)
     for refine in (1, 2):
         sv, prod, _, _ = _run_svd(L, B, left_dir, m, refine)
         assert np.abs(sv - S).max() < 2e-13, "refine=%d" % refine
-        want = ((Q1[:, :m] * S[:m]) @ Q2[:, :m].T).reshape(B.shape)
         assert np.abs(prod - want).max() < 1e-11
+    # refine = 3: all m kept singular values sit in the accurate leading block, so the second pass is deferred to
+    # tnml_svd_split_tail.  The factors are final (and identical) before the tail call; the discarded singular values
+    # reach full accuracy after it.
+    snap = []
+    sv3, prod3, Ap3, Aq3 = _run_svd(L, B, left_dir, m, 3, tail=True, before_tail=snap)
+    sv_before, p_before, q_before = snap[0]
+    assert np.array_equal(p_before, Ap3.reshape(-1)) and np.array_equal(q_before, Aq3.reshape(-1))
+    assert np.abs(prod3 - want).max() < 1e-11
+    assert np.abs(sv_before[:m] - S[:m]).max() < 2e-13
+    assert np.abs(sv3 - S).max() < 2e-13
+    if 2 * min(Dl, Dr) > 64:                       # the cluster path defers; the single-CTA path never does
+        assert np.abs(sv_before - S).max() > np.abs(sv3 - S).max()
 
 
 def test_svd_rank_deficient(L):
