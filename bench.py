@@ -294,6 +294,16 @@ def main():
                     flops_per_launch="8*Ns*L*Dl*Dr per launch (2 flops x Ns x (2 Dl) x (2 L Dr)), summed over the "
                                      "launches of the timed region / summed CUDA-event time")
 
+    # whole bond update against the FP64 tensor-pipe roofline: algorithmic FLOPs of SURVEY.md section 8d (uniform bond
+    # dimension D in the interior; the chain ends are smaller, so this slightly over-counts) / measured step time
+    if args.dtype == "f64":
+        F_update = Ns * D * D * (16 * L + 4) + 4 * Ns * L * D
+        t_update = ms * 1e-3 / n_updates
+        roofline["whole_update"] = dict(gflop=F_update / 1e9, ideal_ms=F_update / (peak * 1e12) * 1e3 / world,
+                                        measured_ms=t_update * 1e3, frac=F_update / (peak * 1e12) / world / t_update,
+                                        note="all kernels of a bond update incl. the latency-bound SVD split and launch "
+                                             "gaps, against the same FP64 DMMA peak (x n_gpus)")
+
     # ---- end-to-end arm through the reference-facing API (host buffers) -------------------------------
     net.l_pos, net._host_fresh = eng.l_pos, False       # the device arm drove the engine directly
     for _ in range(max(1, min(args.warmup, 2))):

@@ -12,7 +12,7 @@ X = np.random.random((Ns, S)); X = np.stack((np.sin(np.pi * X / 2), np.cos(np.pi
 y = np.random.randint(0, L, Ns)
 with contextlib.redirect_stdout(io.StringIO()):
     net = tn.Network(N=S, M=D, L=L, normalize=True, calibration_X=X, act_fn="linear", loss_fn="MSE",
-                     truncation="fixed", max_bond=D)
+                     truncation="fixed", max_bond=D, dtype=os.environ.get("PDT", "float64"))
 for sw in range(int(os.environ.get("PSW", 3))):
     f = net.forward(X)
     f = net.sweep(X, y, f, 1e-4, 1e-3, left_dir=(net.l_pos == S - 1))
