@@ -199,7 +199,8 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
                                                       int max_sweeps, double tol, int use_chol, int pass_id,
                                                       double* __restrict__ info, double* __restrict__ skip_flag,
                                                       const double* __restrict__ lam_prev, double* __restrict__ Wout,
-                                                      int* __restrict__ flags_out, const int* __restrict__ sub) {
+                                                      int* __restrict__ flags_out, const int* __restrict__ sub,
+                                                      int m_split, int* __restrict__ split_out) {
   if (sub) n = sub[0];                               // sub-block second pass (export mode only)
   // Second-pass protocol: the first pass sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7 (sigma ratio
   // > 3e-4: a single Gram pass is then already accurate to ~1e-12 sigma_max for every singular value); the second
@@ -247,6 +248,8 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     __shared__ double cand_v[NWG];
     __shared__ int cand_i[NWG];
     __shared__ double piv_floor_s;
+    __shared__ double pval[NP];                          // pivot (largest remaining diagonal entry) of every step
+    __shared__ int order[NP];
     const int j = tid % NP, gq = tid / NP;
     for (int jj = tid; jj < NP; jj += NT) { active[jj] = jj < n; diag[jj] = jj < n ? W[jj * NP + jj] : 0.0; }
     __syncthreads();
@@ -281,8 +284,11 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     pick(pbest, c);
     const double piv_floor = pbest * (double)n * 2.220446049250313e-16;
     if (tid == 0) piv_floor_s = piv_floor;
+    int kdone = 0;
     for (int k = 0; k < n; ++k) {
       if (c < 0 || !(pbest > piv_floor)) break;          // numerically rank deficient from here on (uniform)
+      kdone = k + 1;
+      if (tid == 0) pval[k] = pbest;
       // this group's share of sum_m R_m[c] R_m[j]; four accumulators: the FP64 FMA latency (~36 cycles) is what
       // bounds this loop, not its throughput
       double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
@@ -337,12 +343,36 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     const double tiny = sqrt(piv_floor_s);
     for (int e = tid; e < NP * NP; e += NT)
       if (active[e / NP]) W[e] = (e / NP == e % NP) ? tiny : 0.0;
+    if (Wout && tid == 0) {
+      // If the pivots drop by more than 2.5e-5 (sigma ratio 5e-3) exactly at the truncation point m_split = n / 2, the
+      // factor is exported in PIVOT order (row k of the factor -> row k: the m_split large rows first) and the sweeps
+      // may treat the two halves as groups (k_jacobi_cluster_w8, two-group schedule).
+      int o = 0;
+      for (int k = 0; k < kdone; ++k) order[o++] = piv[k];
+      for (int r = 0; r < NP; ++r)
+        if (r >= n || active[r]) order[o++] = r;
+      int sp = 0;
+      if (split_out && m_split > 0 && n == 2 * m_split && (m_split & 7) == 0 && kdone >= m_split &&
+          (kdone == m_split || pval[m_split] < 2.5e-5 * pval[m_split - 1]))
+        sp = m_split;
+      if (split_out) split_out[0] = sp;
+      // without a usable gap the rows stay where they are (scattered by pivot): measured 8.1 against 8.8 sweeps of the
+      // plain cyclic schedule on the bench workload
+      if (sp == 0)
+        for (int r = 0; r < NP; ++r) order[r] = r;
+    }
     __syncthreads();
+    if (Wout) {                                      // export mode
+      for (int e = tid; e < NP * NP; e += NT) Wout[e] = W[order[e / NP] * NP + e % NP];
+      for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
+      return;
+    }
   }
 
-  if (Wout) {                                        // export mode
+  if (Wout) {                                        // export mode without preconditioning
     for (int e = tid; e < NP * NP; e += NT) Wout[e] = W[e];
     for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
+    if (split_out && tid == 0) split_out[0] = 0;
     return;
   }
 
@@ -963,7 +993,8 @@ template <int E, int K>
 __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ Wg, double* __restrict__ nrm2g,
                                                            int* __restrict__ flags, int max_sweeps, double tol,
                                                            double* __restrict__ info, const double* __restrict__ skip_flag,
-                                                           int pass_id, const int* __restrict__ sub, int mixed) {
+                                                           int pass_id, const int* __restrict__ sub, int mixed,
+                                                           const int* __restrict__ split) {
   constexpr int NP = 32 * E, NBmax = NP / K, KT = 32 * K;   // KT = threads of one block pair
   extern __shared__ __align__(16) double sm[];   // per block pair: 2K rows x NP, then 2K norms
   if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
@@ -989,6 +1020,19 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
   int ra = (bp == 0) ? 0 : bp - 1, rb = NB - 2 - bp;
   int sweeps_done = 0;
   bool fast = mixed != 0;
+  // Two-group schedule (split != nullptr and *split == NB K / 2): the Cholesky export found a gap of > 5e-3 in sigma
+  // exactly at the truncation point -- the spectrum of a trained bond tensor: D singular values of order 1, the rest
+  // ~1e-6 -- and wrote the rows in pivot order, so blocks [0, NB/2) hold the large rows and [NB/2, NB) the small ones.
+  // Phase A sweeps inside the two groups at the same time (4 + 4 block pairs, 63 instead of 127 rotation sets per
+  // sweep at n = 128) until both have converged, phase X rotates every (large, small) pair once (64 sets); A and X
+  // alternate until an X sweep finds no pair above 1e-8 (cross couplings converge quadratically from the gap).
+  // Measured on dumped bond tensors: 758 instead of 1143-1270 sequential rotation sets.
+  const int nbg = NB / 2;                                          // blocks per group
+  const bool two_group = split != nullptr && sub == nullptr && (NB % 4 == 0) && __ldcg(split) == nbg * K;
+  const int hp = nbg / 2;                                          // block pairs per group in phase A
+  const int grp = (hp > 0) ? bp / hp : 0, lp = (hp > 0) ? bp % hp : 0;
+  int la = (lp == 0) ? 0 : lp - 1, lb = nbg - 2 - lp;
+  int mode = two_group ? 1 : 0;                                    // 0 plain, 1 phase A, 2 phase X
 
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     for (int r = gwarp; r < NB * K; r += nwarps) {   // refresh the cached squared row norms
@@ -1000,10 +1044,13 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
     }
     cl.sync();
     int rotated = 0;
-    for (int round = 0; round < NB - 1; ++round) {
+    const int nrounds = mode == 0 ? NB - 1 : (mode == 1 ? nbg - 1 : nbg);
+    for (int round = 0; round < nrounds; ++round) {
       if (active) {
-        const int bi = (bp == 0) ? 0 : 1 + ra;
-        const int bj = 1 + rb;
+        int bi, bj;
+        if (mode == 0) { bi = (bp == 0) ? 0 : 1 + ra; bj = 1 + rb; }
+        else if (mode == 1) { bi = grp * nbg + ((lp == 0) ? 0 : 1 + la); bj = grp * nbg + 1 + lb; }
+        else { bi = bp; bj = nbg + (bp + round) % nbg; }
         // stage: warp w brings row w of each block (rows 0..K-1 = block bi, K..2K-1 = block bj)
         double* const ga_ = Wg + (size_t)(K * bi + w) * NP + lane;
         double* const gb_ = Wg + (size_t)(K * bj + w) * NP + lane;
@@ -1014,7 +1061,7 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
         }
         if (lane == 0) { nr[w] = __ldcg(nrm2g + K * bi + w); nr[K + w] = __ldcg(nrm2g + K * bj + w); }
         pair_barrier_n(1 + bpl, KT);
-        if (round == 0) {   // the K(K-1)/2 pairs inside each block, once per sweep: round-robin of K players, K-1 sets
+        if (round == 0 && mode != 2) {   // the K(K-1)/2 pairs inside each block, once per sweep: round-robin, K-1 sets
           const int base = (w / (K / 2)) * K, j = w % (K / 2);
 #pragma unroll 1
           for (int s = 0; s < K - 1; ++s) {
@@ -1041,8 +1088,13 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
           gb_[32 * k] = rows[(K + w) * NP + lane + 32 * k];
         }
         if (lane == 0) { nrm2g[K * bi + w] = nr[w]; nrm2g[K * bj + w] = nr[K + w]; }
-        ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
-        rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+        if (mode == 0) {
+          ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+          rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+        } else if (mode == 1) {
+          la = (la + 1 == nbg - 1) ? 0 : la + 1;
+          lb = (lb + 1 == nbg - 1) ? 0 : lb + 1;
+        }
       }
       cl.sync();
     }
@@ -1051,8 +1103,15 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
     sweeps_done = sweep + 1;
     cl.sync();
     const int any = __ldcg(flags + sweep);
-    if (!(any & 1)) break;
-    fast = mixed != 0 && (any & 2) != 0;                           // FP32 inner products while some pair is above 1e-2
+    if (mode == 0) {
+      if (!(any & 1)) break;
+    } else if (mode == 1) {
+      if (!(any & 1)) mode = 2;                                    // both groups converged: couple them
+    } else {
+      if (!(any & 1)) break;                                       // no cross pair above 1e-8: done
+      mode = 1;
+    }
+    fast = mixed != 0 && (any & 2) != 0;                           // FP32 inner products while some pair is above 5e-2
   }
   if (gwarp == 0 && lane == 0 && info) info[0] = (double)sweeps_done;
 }
@@ -1166,7 +1225,8 @@ __global__ void k_jacobi_cluster(double*, double*, int*, int, double, double*, c
 template <int E>
 __global__ void k_jacobi_cluster_w(double*, double*, int*, int, double, double*, const double*, int, const int*);
 template <int E, int K>
-__global__ void k_jacobi_cluster_w8(double*, double*, int*, int, double, double*, const double*, int, const int*, int);
+__global__ void k_jacobi_cluster_w8(double*, double*, int*, int, double, double*, const double*, int, const int*, int,
+                                    const int*);
 
 constexpr int CHOL_BIG_CAP_256 = 100, CHOL_BIG_CAP_512 = 50;   // factor rows cached in shared memory (~200 KB)
 
@@ -1240,7 +1300,7 @@ static cudaError_t launch_cluster_w(int ctas, int threads, double* Wg, double* n
 // K rows per block; NP / (2K) block pairs of K warps each, spread over the CTAs of one cluster (512 threads per CTA at most)
 template <int E, int K>
 static cudaError_t launch_cluster_w8(double* Wg, double* nrm2g, int* flags, double tol, double* info, const double* skip,
-                                     int pass_id, const int* sub, int mixed, cudaStream_t st) {
+                                     int pass_id, const int* sub, int mixed, cudaStream_t st, const int* split = nullptr) {
   constexpr int NP = 32 * E, pairs = NP / (2 * K), max_ctas = (E == 16) ? 16 : 8;   // 16: non-portable cluster size
   constexpr int ctas = pairs < max_ctas ? pairs : max_ctas, per_cta = pairs / ctas, threads = per_cta * 32 * K;
   static_assert(threads <= 512 && per_cta * ctas == pairs, "cluster shape");
@@ -1258,7 +1318,16 @@ static cudaError_t launch_cluster_w8(double* Wg, double* nrm2g, int* flags, doub
   cfg.numAttrs = 1;
   int max_sweeps = 60;
   return cudaLaunchKernelEx(&cfg, k_jacobi_cluster_w8<E, K>, Wg, nrm2g, flags, max_sweeps, tol, info, skip, pass_id, sub,
-                            mixed);
+                            mixed, split);
+}
+
+static int jacobi_two_group_enabled() {   // TNML_JACOBI_TWO_GROUP=0: always the plain cyclic schedule (A/B knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_JACOBI_TWO_GROUP");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
 }
 
 static int chol_big_enabled() {   // TNML_CHOL_BIG=0: no Cholesky preconditioning for n > 128 (A/B knob)
@@ -1303,22 +1372,23 @@ struct JacobiBuffers {
 // (the small singular values) is decomposed -- the partials then hold that block's Gram matrix.
 static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
                          int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
-                         cudaStream_t st, int m_defer = 0) {
+                         cudaStream_t st, int m_defer = 0, int m_keep = 0, int* split_slot = nullptr) {
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) {
     TNML_COUNT(1);
     if (n > 64)
       k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                   lam_prev, nullptr, nullptr, nullptr);
+                                                   lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
     else if (n > 32)
       k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                lam_prev, nullptr, nullptr, nullptr);
+                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
     else
       k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                lam_prev, nullptr, nullptr, nullptr);
+                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
     return tnml_launch_status();
   }
   const int* sub2 = (pass_id >= 2) ? sub : nullptr;   // sub-block mode of the second pass
+  int* split = nullptr;                               // device flag of the two-group schedule (first pass, n <= 128)
   cudaError_t e;
   int NP;
   TNML_COUNT(3);
@@ -1330,8 +1400,10 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
       TNML_COUNT(1);
       k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, nparts, n, n, scratch, jb.flags, skip, pass_id, sub2,
                                                             1);
+      // only the first pass of a split that keeps m = n / 2 singular triplets may sweep in two groups
+      split = (pass_id == 1 && split_slot && m_keep > 0 && jacobi_two_group_enabled()) ? split_slot : nullptr;
       k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(scratch, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info, skip,
-                                                   lam_prev, jb.Wg, jb.flags, sub2);
+                                                   lam_prev, jb.Wg, jb.flags, sub2, m_keep, split);
     } else {
       k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id,
                                                               sub2, 0);
@@ -1339,7 +1411,8 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
     const int jv = jacobi_variant();
     if (jv >= 2 && jacobi_block_rows() == 16)
       e = launch_cluster_w8<4, 16>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
-    else if (jv >= 2) e = launch_cluster_w8<4, 8>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st);
+    else if (jv >= 2)
+      e = launch_cluster_w8<4, 8>(jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, jv == 3, st, split);
     else if (jv == 1) e = launch_cluster_w<4>(8, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
     else e = launch_cluster<4, 4>(4, 128, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   } else {
@@ -1485,7 +1558,7 @@ static SvdPlan svd_plan_rc(int R, int C) {
   p.off_Wg = o; o += (size_t)p.NP * p.NP;
   p.off_nrm = o; o += p.NP;
   p.off_flags = o; o += 32;   // 64 ints
-  p.off_sub = o; o += 1;      // 2 ints
+  p.off_sub = o; o += 2;      // 4 ints: {ns, k0} of the second pass, the two-group split flag, spare
   p.total = o;
   return p;
 }
@@ -1526,7 +1599,8 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
 
   TNML_COUNT(1);
   k_gram<<<ggrid, 256, 0, st>>>(X, ss, sl, n, Nl, p.lc, partial, nullptr, nullptr);
-  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer);
+  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer, m,
+                     (int*)(w + p.off_sub) + 2);
   if (rc) return rc;
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
