@@ -87,7 +87,8 @@ int tnml_site_predict(const void* Lenv, const void* phi_p, const void* A_label, 
  * fa = act(f / T) (NC:767-796, softmax NOT max-stabilised), g = dloss(fa, onehot(y)) (NC:800-835),
  * q[b][l][2*sigma+tau] = g[b][l] * phi_p[b][sigma] * phi_q[b][tau]   (operand of the gradient GEMM)
  * pp[b][2*sigma+tau]   = phi_p[b][sigma] * phi_q[b][tau]             (operand of the projection epilogue)
- * metrics[0] = number of samples with argmax(fa) == y, metrics[1] = sum |onehot(y) - fa|   (NC:697-702)
+ * metrics[0] = number of samples with argmax(fa) == y, metrics[1] = sum |onehot(y) - fa|   (NC:697-702),
+ * metrics[2] = Ns (the local sample count, so that the sharded sums can be all-reduced as they are), metrics[3] = 0
  * The two sums are reduced in a fixed order (deterministic).  ws: tnml_act_lossder_workspace_bytes(Ns). */
 int64_t tnml_act_lossder_workspace_bytes(int64_t Ns);
 int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const void* phi_q, void* q, void* pp,

@@ -226,6 +226,7 @@ class Network():
             import torch
             host = np.ascontiguousarray(np.asarray(f.elem, dtype=np.float64).T)
             eng.f_buf[eng.f_cur].copy_(torch.from_numpy(host.reshape(-1)))      # converts to the per-sample dtype
+            eng._ald_for = None                                                # computed ahead from the old prediction
 
     def _after_steps(self, var_hist, debug, L2_flag):
         eng = self._eng

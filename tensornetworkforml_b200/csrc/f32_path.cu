@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) k_metrics_final_f32(const double* __restrict__ partial, int nblocks,
-                                                          double* __restrict__ metrics) {
+                                                          double* __restrict__ metrics, double count) {
   __shared__ double red[2][256];
   double a = 0.0, e = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; e += partial[2 * i + 1]; }
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(256) k_metrics_final_f32(const double* __restr
     if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; }
+  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = 0.0; }
 }
 
 // f[b][l] = sum L[b][a] phi[b][s] A[a][s][l][c] R[b][c]; thin kernel (forward() calls it with Dl == 1 or Dr == 1)
@@ -887,7 +887,7 @@ int act_lossder(const float* f, const int32_t* y, const float* phi_p, const floa
   const int nb = tnml_cdiv(Ns, 256);
   TNML_COUNT(2);
   k_act_lossder_f32<<<nb, 256, 0, st>>>(f, y, (const float2*)phi_p, (const float2*)phi_q, g, pp, ws, Ns, L, act, loss, T);
-  k_metrics_final_f32<<<1, 256, 0, st>>>(ws, nb, metrics);
+  k_metrics_final_f32<<<1, 256, 0, st>>>(ws, nb, metrics, (double)Ns);
   return tnml_launch_status();
 }
 

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) k_loss_der(const double* __restrict__ fa,
 
 // fixed-order final sum of the per-block partials (one block)
 __global__ void __launch_bounds__(256) k_metrics_final(const double* __restrict__ partial, int nblocks,
-                                                      double* __restrict__ metrics) {
+                                                      double* __restrict__ metrics, double count) {
   __shared__ double red[2][256];
   double a = 0.0, e = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; e += partial[2 * i + 1]; }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_metrics_final(const double* __restrict_
     if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; }
+  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -280,7 +280,7 @@ extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi
                                                             (const double2*)phi_q, (double*)q, (double*)pp, (double*)ws,
                                                             Ns, L, act, loss, T);
   TNML_COUNT(1);
-  k_metrics_final<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)ws, nb, (double*)metrics);
+  k_metrics_final<<<1, 256, 0, (cudaStream_t)stream>>>((const double*)ws, nb, (double*)metrics, (double)Ns);
   return tnml_launch_status();
 }
 

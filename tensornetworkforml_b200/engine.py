@@ -126,6 +126,7 @@ class SweepEngine:
         # normal-priority stream after the split (tnml_svd_split refine = 3 + tnml_svd_split_tail); two workspaces
         # alternate so that the next split does not wait for it
         self.defer_tail = True
+        self._ald_for = None          # (p, left_dir) whose activation / loss derivative was computed ahead (split_phase)
         self._tail = None
         self._tail_evt = [None, None]
 
@@ -268,6 +269,7 @@ class SweepEngine:
                 pin.copy_(Xh)
                 Xd.copy_(pin, non_blocking=True)
         assert Xd.numel() == Ns * self.S * 2, "input must have shape (Ns, S, 2)"
+        self._ald_for = None
         self._alloc_batch(Ns)
         call("tnml_pack_features", _ptr(Xd), _ptr(self.phi), Ns, self.S, self.DT, self._stream())
         self.h2d_bytes = Ns * self.S * 2 * 8
@@ -310,6 +312,7 @@ class SweepEngine:
 
     def forward(self):
         S, l = self.S, self.l_pos
+        self._ald_for = None
         if l == 0:
             for p in range(S - 1, 0, -1):
                 self._advance_left(p)
@@ -327,6 +330,7 @@ class SweepEngine:
 
     # ------------------------------------------------------------------ sweep  (NC:384-436)
     def set_labels(self, y):
+        self._ald_for = None
         if isinstance(y, torch.Tensor) and y.is_cuda:
             self.y_dev = y.to(torch.int32).contiguous()
         else:
@@ -375,6 +379,7 @@ class SweepEngine:
         nb = max(_lib.lib().tnml_svd_split_workspace_bytes(cap, cap, self.L, d) for d in (0, 1))
         self._workspace("svd0", nb)
         self._workspace("svd1", nb)
+        self._workspace("gbuf", (cap * 4 * self.L * cap + 4) * 8)   # largest [dB | metrics] of the chain, never re-sized
         self._label_to("L" if left_dir else "R")
         if L2_flag:
             self._build_norm_stack(left_dir)
@@ -388,6 +393,13 @@ class SweepEngine:
         """One bond update (NC:440-573 with update_B NC:577-763); everything stays on the device."""
         ctx = self.update_phase(lr, weight_dec, L2_flag, left_dir)
         return self.split_phase(ctx)
+
+    def _act_lossder(self, p, q, met):
+        """q, pp and the metric sums of the pair (p, q) from the current prediction f (NC:694-707)."""
+        ws = self._workspace("al", _lib.lib().tnml_act_lossder_workspace_bytes(self.Ns))
+        call("tnml_act_lossder", _ptr(self.f_buf[self.f_cur]), _ptr(self.y_dev), self._phi(p), self._phi(q),
+             _ptr(self.q_buf), _ptr(self.pp_buf), _ptr(met), _ptr(ws), self.Ns, self.L, self.act, self.loss, self.T,
+             self.DT, self._stream())
 
     def update_phase(self, lr, weight_dec, L2_flag, left_dir, B_override=None):
         """update_B (NC:577-763): environment advance, loss derivative + metrics, gradient, regularisation, clipping,
@@ -434,18 +446,19 @@ class SweepEngine:
         if left_dir and q < S - 1:
             self._advance_left(q + 1)
         # activation, loss derivative, metrics                                              NC:694-707
-        f_in = self.f_buf[self.f_cur]
         gbuf = self._workspace("gbuf", (nB + 4) * 8)
         dB, met = gbuf[:nB], gbuf[nB:nB + 4]
-        ws = self._workspace("al", _lib.lib().tnml_act_lossder_workspace_bytes(Ns))
-        call("tnml_act_lossder", _ptr(f_in), _ptr(self.y_dev), self._phi(p), self._phi(q), _ptr(self.q_buf),
-             _ptr(self.pp_buf), _ptr(met), _ptr(ws), Ns, L, self.act, self.loss, self.T, self.DT, st)
+        if self._ald_for == (p, left_dir):
+            self._ald_for = None          # computed ahead by the previous split_phase, behind the SVD split
+        else:
+            self._act_lossder(p, q, met)
         # gradient: K = Ns tensor-core reduction                                             NC:625-646, NC:710
         ws = self._workspace("grad", _lib.lib().tnml_grad_workspace_bytes(Ns, Dl, Dr, L))
         with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
             call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L,
                  self.DT, st)
-        reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world)   # one collective per update
+        reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world,   # one collective per update
+                                    count_written=True)
         self.hist["metrics"][step].copy_(met)
         # regularisation, clipping, update                                                   NC:728-761
         if side is not main:
@@ -504,6 +517,20 @@ class SweepEngine:
                 evt.record(tail)
             self._tail_evt[par] = evt
         self.f_cur = 1 - self.f_cur
+        # the next bond update's activation / loss derivative / metrics only need the new prediction: enqueue them now,
+        # so that they run while the SVD split is still busy on the side stream
+        pn = p - 1 if left_dir else p + 1
+        if side is not main and 0 <= pn and pn + 1 <= S - 1:
+            Dln = self.bonds[pn] if not left_dir else self.bonds[pn]
+            Drn = self.bonds[pn + 2]
+            if not left_dir:
+                Dln = m                                  # the bond between p and q has just been set to m
+            else:
+                Drn = m
+            nBn = Dln * 4 * L * Drn
+            gb = self._workspace("gbuf", (nBn + 4) * 8)
+            self._act_lossder(pn, pn + 1, gb[nBn:nBn + 4])
+            self._ald_for = (pn, left_dir)
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
             self._inflight = ctx                        # keep B, B', G alive until the main stream has passed the wait

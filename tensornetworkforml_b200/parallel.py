@@ -23,12 +23,14 @@ def shard_bounds(Ns: int, rank: int, world: int):
     return rank * Ns // world, (rank + 1) * Ns // world
 
 
-def reduce_gradient_and_metrics(buf: torch.Tensor, n_grad: int, local_count: int, group=None, world: int = 1):
+def reduce_gradient_and_metrics(buf: torch.Tensor, n_grad: int, local_count: int, group=None, world: int = 1,
+                                count_written: bool = False):
     """``buf[:n_grad]`` = local dB, ``buf[n_grad]`` = local n_correct, ``buf[n_grad+1]`` = local sum|y-f|.
     Writes the local sample count into ``buf[n_grad+2]`` and sums the first ``n_grad + N_EXTRA`` entries over the
     group in place (a single collective per bond update)."""
-    buf[n_grad + 2:n_grad + N_EXTRA].zero_()
-    buf[n_grad + 2:n_grad + 3].fill_(float(local_count))
+    if not count_written:        # tnml_act_lossder writes [.., count, 0] itself: no extra launches on the critical path
+        buf[n_grad + 2:n_grad + N_EXTRA].zero_()
+        buf[n_grad + 2:n_grad + 3].fill_(float(local_count))
     if world > 1:
         dist.all_reduce(buf[:n_grad + N_EXTRA], op=dist.ReduceOp.SUM, group=group)
     return buf
