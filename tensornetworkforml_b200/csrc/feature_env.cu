@@ -1,4 +1,6 @@
 // Feature map, input packing, environment advance (FP64 DMMA), forward's last contraction.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "f32_path.cuh"
 
@@ -131,6 +133,105 @@ __global__ void __launch_bounds__(128) k_env_advance(const double* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Environment advance, persistent TMA-staged version for K <= 64, M <= 64 (K % 4 == 0, M even): the site tensor W is
+// staged ONCE per CTA in shared memory and the environment rows stream through a 3-stage ring, both with bulk
+// asynchronous copies (cp.async.bulk, the 1-D TMA path: SASS UBLKCP) that complete on mbarriers -- one copy per
+// (padded) row, so the DMMA fragment loads stay bank-conflict free (row strides = 8 mod 16 doubles / 4 mod 16).
+// CTA = 8 warps = 4 (16 samples each) x 2 (32 output columns each, both sigma planes); tile = 64 samples.
+// ---------------------------------------------------------------------------------------------------
+constexpr int EB_BM = 64, EB_STAGES = 3, EB_ES = 68, EB_WS = 136;
+constexpr int EB_SMEM_BYTES = (64 * EB_WS + EB_STAGES * EB_BM * EB_ES) * 8;
+
+__global__ void __launch_bounds__(256, 1) k_env_advance_tma(const double* __restrict__ E, const double2* __restrict__ phi,
+                                                           const double* __restrict__ W, double* __restrict__ out,
+                                                           int64_t Ns, int K, int M) {
+  extern __shared__ __align__(16) double smem[];
+  double* Ws = smem;                         // [64][EB_WS]: W[k][sigma][m] at k*EB_WS + sigma*64 + m
+  double* Es = smem + 64 * EB_WS;            // EB_STAGES x [EB_BM][EB_ES]
+  __shared__ __align__(8) uint64_t wbar, full[EB_STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = warp >> 1, wc = warp & 1;   // 16-row group, 32-column half
+  const int ntiles = (int)((Ns + EB_BM - 1) / EB_BM);
+
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    for (int s = 0; s < EB_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  // columns m >= M of W are never copied: they must read as zero
+  for (int e = tid; e < 64 * EB_WS; e += 256) Ws[e] = 0.0;
+  fence_proxy_async();                       // generic-proxy zeros before the async-proxy copies into the same rows
+  __syncthreads();
+  auto issue = [&](int tile, int s) {        // warp 0: one bulk copy per environment row of the tile
+    const int64_t b0 = (int64_t)tile * EB_BM;
+    const int rows = (int)min((int64_t)EB_BM, Ns - b0);
+    if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(rows * K * 8));
+    __syncwarp();
+    for (int r = lane; r < rows; r += 32)
+      tma_bulk_g2s(Es + ((size_t)s * EB_BM + r) * EB_ES, E + (b0 + r) * K, (unsigned)(K * 8), &full[s]);
+  };
+  if (warp == 0) {
+    if (lane == 0) mbar_expect_tx(&wbar, (unsigned)(K * 2 * M * 8));
+    __syncwarp();
+    for (int i = lane; i < 2 * K; i += 32) {
+      const int k = i >> 1, sg = i & 1;
+      tma_bulk_g2s(Ws + (size_t)k * EB_WS + sg * 64, W + ((size_t)k * 2 + sg) * M, (unsigned)(M * 8), &wbar);
+    }
+    int tile = blockIdx.x;
+    for (int s = 0; s < EB_STAGES - 1 && tile < ntiles; ++s, tile += gridDim.x) issue(tile, s);
+  }
+  mbar_wait(&wbar, 0);
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int s = it % EB_STAGES;
+    mbar_wait(&full[s], (it / EB_STAGES) & 1);
+    const double* Et = Es + (size_t)s * EB_BM * EB_ES;
+    double acc[2][2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[i][sg][n][0] = acc[i][sg][n][1] = 0.0;
+    for (int k4 = 0; k4 < K; k4 += 4) {
+      const double a0 = Et[(wr * 16 + g) * EB_ES + k4 + t];
+      const double a1 = Et[(wr * 16 + 8 + g) * EB_ES + k4 + t];
+#pragma unroll
+      for (int sg = 0; sg < 2; ++sg)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const double bv = Ws[(k4 + t) * EB_WS + sg * 64 + wc * 32 + n * 8 + g];
+          dmma(acc[0][sg][n][0], acc[0][sg][n][1], a0, bv);
+          dmma(acc[1][sg][n][0], acc[1][sg][n][1], a1, bv);
+        }
+    }
+    const int64_t b0 = (int64_t)tile * EB_BM;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t b = b0 + wr * 16 + i * 8 + g;
+      if (b < Ns) {
+        const double2 p = phi[b];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int m = wc * 32 + n * 8 + 2 * t;
+          if (m + 1 < M) {
+            *reinterpret_cast<double2*>(out + b * M + m) =
+                make_double2(p.x * acc[i][0][n][0] + p.y * acc[i][1][n][0], p.x * acc[i][0][n][1] + p.y * acc[i][1][n][1]);
+          } else if (m < M) {
+            out[b * M + m] = p.x * acc[i][0][n][0] + p.y * acc[i][1][n][0];
+          }
+        }
+      }
+    }
+    __syncthreads();                         // every warp is done with stage s: refill it with the tile 2 rounds ahead
+    const int64_t nxt = (int64_t)tile + (int64_t)(EB_STAGES - 1) * gridDim.x;
+    if (warp == 0 && nxt < ntiles) issue((int)nxt, (it + EB_STAGES - 1) % EB_STAGES);
+  }
+}
+
 // Wt[c][s][a] = site[a][s][c]
 __global__ void k_site_transpose(const double* __restrict__ site, double* __restrict__ Wt, int Dl, int Dr) {
   int n = Dl * 2 * Dr;
@@ -217,6 +318,22 @@ extern "C" int tnml_env_advance(const void* E, const void* phi_p, const void* W,
     return f32::env_advance((const float*)E, (const float*)phi_p, (const float*)W, (float*)out, Ns, K, M,
                             (cudaStream_t)stream);
   TNML_COUNT(1);
+  static int use_tma = -1;                   // TNML_ENV_TMA=0: always the plain kernel (A/B knob)
+  if (use_tma < 0) {
+    const char* ev = getenv("TNML_ENV_TMA");
+    use_tma = (ev && atoi(ev) == 0) ? 0 : 1;
+    if (use_tma) {
+      cudaError_t e = cudaFuncSetAttribute(k_env_advance_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_BYTES);
+      if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    }
+  }
+  if (use_tma && K <= 64 && M <= 64 && K % 4 == 0 && M % 2 == 0 && Ns >= 4 * EB_BM &&
+      (((uintptr_t)E | (uintptr_t)W | (uintptr_t)out) & 15) == 0) {
+    const int ntiles = tnml_cdiv(Ns, EB_BM);
+    k_env_advance_tma<<<ntiles < kNumSMs ? ntiles : kNumSMs, 256, EB_SMEM_BYTES, (cudaStream_t)stream>>>(
+        (const double*)E, (const double2*)phi_p, (const double*)W, (double*)out, Ns, K, M);
+    return tnml_launch_status();
+  }
   k_env_advance<<<tnml_cdiv(Ns, EA_BM), 128, 0, (cudaStream_t)stream>>>((const double*)E, (const double2*)phi_p,
                                                                        (const double*)W, (double*)out, Ns, K, M);
   return tnml_launch_status();

@@ -73,7 +73,9 @@ def test_feature_map_and_pack(L, Ns, S):
     assert np.array_equal(phi2.cpu().numpy(), want)          # pure data movement: bitwise
 
 
-@pytest.mark.parametrize("Ns,K,M", [(77, 3, 5), (1000, 64, 64), (50, 1, 2), (333, 10, 10), (64, 2, 1), (130, 40, 70)])
+@pytest.mark.parametrize("Ns,K,M", [(77, 3, 5), (1000, 64, 64), (50, 1, 2), (333, 10, 10), (64, 2, 1), (130, 40, 70),
+                                    (5000, 32, 64), (777, 64, 32), (300, 16, 2), (260, 4, 64), (20011, 64, 64),
+                                    (4097, 8, 20)])
 def test_env_advance_both_directions(L, Ns, K, M):
     rng = np.random.default_rng(1)
     E = rng.standard_normal((Ns, K))
