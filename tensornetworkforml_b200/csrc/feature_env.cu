@@ -187,6 +187,13 @@ __global__ void __launch_bounds__(256, 1) k_env_advance_tma(const double* __rest
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
     const int s = it % EB_STAGES;
+    const int64_t b0 = (int64_t)tile * EB_BM;
+    double2 ph[2];                           // the epilogue's phi values: loaded before the MMA loop hides their latency
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t b = b0 + wr * 16 + i * 8 + g;
+      ph[i] = b < Ns ? phi[b] : make_double2(0.0, 0.0);
+    }
     mbar_wait(&full[s], (it / EB_STAGES) & 1);
     const double* Et = Es + (size_t)s * EB_BM * EB_ES;
     double acc[2][2][4][2];
@@ -196,6 +203,7 @@ __global__ void __launch_bounds__(256, 1) k_env_advance_tma(const double* __rest
       for (int sg = 0; sg < 2; ++sg)
 #pragma unroll
         for (int n = 0; n < 4; ++n) acc[i][sg][n][0] = acc[i][sg][n][1] = 0.0;
+#pragma unroll 2
     for (int k4 = 0; k4 < K; k4 += 4) {
       const double a0 = Et[(wr * 16 + g) * EB_ES + k4 + t];
       const double a1 = Et[(wr * 16 + 8 + g) * EB_ES + k4 + t];
@@ -208,12 +216,11 @@ __global__ void __launch_bounds__(256, 1) k_env_advance_tma(const double* __rest
           dmma(acc[1][sg][n][0], acc[1][sg][n][1], a1, bv);
         }
     }
-    const int64_t b0 = (int64_t)tile * EB_BM;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int64_t b = b0 + wr * 16 + i * 8 + g;
       if (b < Ns) {
-        const double2 p = phi[b];
+        const double2 p = ph[i];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const int m = wc * 32 + n * 8 + 2 * t;
