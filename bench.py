@@ -120,7 +120,8 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                          "--format=csv,noheader,nounits", "-lms",
+                                          os.environ.get("TNML_BENCH_SMI_MS", "100")], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -233,7 +234,6 @@ def main():
         device_step()
     barrier()
     clocks = ClockSampler(local_rank)
-    eng.timers = {}
     k0 = lib.tnml_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -244,6 +244,16 @@ def main():
     launches = lib.tnml_kernel_launches() - k0
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
+    # per-kernel live timing in a SECOND pass of the same K steps (the event pairs around every call would perturb the
+    # headline number of the short-step configurations); `share` below is relative to that pass
+    eng.timers = {}
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for _ in range(args.steps):
+        device_step()
+    t1e.record()
+    barrier()
+    ms_timed_pass = t0e.elapsed_time(t1e)
     timers, eng.timers = eng.timers, None
     t = torch.tensor([ms], dtype=torch.float64, device=eng.device)
     if world > 1:
@@ -266,7 +276,8 @@ def main():
     for name, evs in timers.items():
         tot = sum(a.elapsed_time(b) for a, b, _ in evs)
         fl = sum(f for _, _, f in evs)
-        kern[name] = dict(calls=len(evs), ms_total=tot, share=tot / ms, tflops=(fl / (tot * 1e-3) / 1e12) if tot else 0.0,
+        kern[name] = dict(calls=len(evs), ms_total=tot, share=tot / ms_timed_pass,
+                          tflops=(fl / (tot * 1e-3) / 1e12) if tot else 0.0,
                           avg_ms=tot / max(1, len(evs)))
     peak = 37.06
     peak_src = "fallback constant (profiles/fp64_peak_r01.json missing)"

@@ -164,8 +164,21 @@ int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_
 int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
                    int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream);
 
-int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir,
-                        int32_t dtype, tnml_stream_t stream);
+/* tnml_svd_split_ev: the same call with a cudaEvent_t (as void*, may be NULL) that is recorded on `stream` once the Gram
+ * matrix is complete, right before the Cholesky kernel that also reserves the SMs of the sweeps' thread-block cluster:
+ * a caller that runs the projection on another stream makes it wait for this event, so that the projection cannot fill
+ * those SMs first.  For sizes that take another path the event is not recorded (create it in the recorded state). */
+int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
+                      int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype, tnml_stream_t stream,
+                      void* gram_done_event);
+/* record: NULL = refine now (second pass on the small block, svals complete when this call has run); otherwise a device
+ * buffer of tnml_svd_tail_record_bytes() bytes that only receives the small block's Gram matrix (no cluster kernel on
+ * this path) -- tnml_svd_tail_batch then solves `nrec` consecutive records at once, one CTA each, and writes the tail
+ * singular values into svals + i * svals_stride (doubles) for record i.  Same Dl, Dr, L, m, left_dir as the split. */
+int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, int32_t Dl, int32_t Dr, int32_t L,
+                        int32_t m, int32_t left_dir, int32_t dtype, tnml_stream_t stream);
+int64_t tnml_svd_tail_record_bytes(void);
+int tnml_svd_tail_batch(void* recs, int32_t nrec, void* svals, int64_t svals_stride, int32_t dtype, tnml_stream_t stream);
 
 /* General form for Network.tensor_svd on any 2-D Tensor (NC:839-962): Mx [R][C] -> US [R][m] = U sqrt(S),
  * SVh [m][C] = sqrt(S) Vh; svals as above (min(R,C) + 2 values). */

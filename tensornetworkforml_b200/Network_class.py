@@ -261,7 +261,7 @@ class Network():
             eng.begin_sweep(labels, left_dir, L2_flag)
         else:                                   # keep the norm-environment stacks, restart the per-call record
             eng.set_labels(labels)
-            eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+            eng.hist["n"], eng.hist["nsv"], eng.hist["m"], eng.hist["tail_solved"] = 0, [], [], 0
         f_dev = eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
         self._after_steps(var_hist, debug, L2_flag)
         out = Tensor(elem=f_dev.t().cpu().numpy().astype(np.float64), axes_names=['l', 'b'])
@@ -285,7 +285,7 @@ class Network():
             eng.begin_sweep(labels, left_dir, L2_flag)
         else:
             eng.set_labels(labels)
-            eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+            eng.hist["n"], eng.hist["nsv"], eng.hist["m"], eng.hist["tail_solved"] = 0, [], [], 0
         p = self.l_pos - ldf
         import torch
         Bc = self._bond_to_canonical(B, p)
@@ -305,7 +305,7 @@ class Network():
             else:
                 var_hist[0].append(h["acc"][0])
                 var_hist[1].append(h["mae"][0])
-        eng.hist["n"], eng.hist["nsv"], eng.hist["m"] = 0, [], []
+        eng.hist["n"], eng.hist["nsv"], eng.hist["m"], eng.hist["tail_solved"] = 0, [], [], 0
         Bn = ctx["Bn"].cpu().numpy().reshape(Bc.shape)
         return self._bond_from_canonical(Bn, B, p)
 

@@ -200,8 +200,23 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
                                                       double* __restrict__ info, double* __restrict__ skip_flag,
                                                       const double* __restrict__ lam_prev, double* __restrict__ Wout,
                                                       int* __restrict__ flags_out, const int* __restrict__ sub,
-                                                      int m_split, int* __restrict__ split_out) {
-  if (sub) n = sub[0];                               // sub-block second pass (export mode only)
+                                                      int m_split, int* __restrict__ split_out,
+                                                      long long batch_stride = 0, int hold = 0) {
+  // hold > 1: launched as ONE cluster of `hold` CTAs of which only rank 0 works; the others wait at the cluster barrier
+  // and thereby keep `hold` SMs of one GPC occupied until this kernel ends -- the cluster sweeps that follow on the same
+  // stream then find a GPC with enough free SMs although the projection has filled the rest of the GPU meanwhile
+  // (without it the sweeps' cluster waited for the projection to drain: 0.9 -> 1.4 ms per split).
+  const bool holder = hold > 1;
+  if (holder && cg::this_cluster().block_rank() != 0) {
+    cg::this_cluster().sync();
+    return;
+  }
+  if (batch_stride > 0) {   // batched form (tnml_svd_tail_batch): block b works on the record b * batch_stride doubles on
+    const size_t off = (size_t)blockIdx.x * (size_t)batch_stride;
+    partial += off; Vt += off; lam += off; info += off; skip_flag += off;
+    sub = reinterpret_cast<const int*>(reinterpret_cast<const double*>(sub) + off);
+  }
+  if (sub) n = sub[0];                               // sub-block second pass
   // Second-pass protocol: the first pass sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7 (sigma ratio
   // > 3e-4: a single Gram pass is then already accurate to ~1e-12 sigma_max for every singular value); the second
   // pass sees the flag, returns the identity rotation and the first-pass eigenvalues.
@@ -213,6 +228,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
       for (int e = threadIdx.x; e < n; e += blockDim.x) lam[e] = lam_prev[e];
       if (threadIdx.x == 0 && info) info[0] = 0.0;
     }
+    if (holder) cg::this_cluster().sync();
     return;
   }
   constexpr int NB = NP / 4;           // row blocks
@@ -365,6 +381,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     if (Wout) {                                      // export mode
       for (int e = tid; e < NP * NP; e += NT) Wout[e] = W[order[e / NP] * NP + e % NP];
       for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
+      if (holder) cg::this_cluster().sync();
       return;
     }
   }
@@ -373,6 +390,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     for (int e = tid; e < NP * NP; e += NT) Wout[e] = W[e];
     for (int e = tid; e < 64; e += NT) flags_out[e] = 0;
     if (split_out && tid == 0) split_out[0] = 0;
+    if (holder) cg::this_cluster().sync();
     return;
   }
 
@@ -1330,6 +1348,15 @@ static int jacobi_two_group_enabled() {   // TNML_JACOBI_TWO_GROUP=0: always the
   return v;
 }
 
+static int gpc_hold_enabled() {   // TNML_SVD_GPC_HOLD=0: plain single-CTA Cholesky launch (A/B knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_SVD_GPC_HOLD");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
 static int chol_big_enabled() {   // TNML_CHOL_BIG=0: no Cholesky preconditioning for n > 128 (A/B knob)
   static int v = -1;
   if (v < 0) {
@@ -1372,7 +1399,8 @@ struct JacobiBuffers {
 // (the small singular values) is decomposed -- the partials then hold that block's Gram matrix.
 static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
                          int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
-                         cudaStream_t st, int m_defer = 0, int m_keep = 0, int* split_slot = nullptr) {
+                         cudaStream_t st, int m_defer = 0, int m_keep = 0, int* split_slot = nullptr,
+                         cudaEvent_t gram_done = nullptr) {
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) {
     TNML_COUNT(1);
@@ -1402,8 +1430,33 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
                                                             1);
       // only the first pass of a split that keeps m = n / 2 singular triplets may sweep in two groups
       split = (pass_id == 1 && split_slot && m_keep > 0 && jacobi_two_group_enabled()) ? split_slot : nullptr;
-      k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(scratch, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info, skip,
-                                                   lam_prev, jb.Wg, jb.flags, sub2, m_keep, split);
+      if (pass_id == 1 && gpc_hold_enabled()) {
+        // the Cholesky runs in CTA 0 of a cluster of 8 whose other CTAs only hold their SMs (see k_jacobi, `hold`);
+        // gram_done lets the caller start the projection at this point, so that it cannot take those SMs first
+        if (gram_done) cudaEventRecord(gram_done, st);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8);
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = 128 * 128 * 8;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 8;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const double* scratch_c = scratch;
+        const double* lam_prev_c = lam_prev;
+        const int* sub_c = sub2;
+        cudaError_t ce = cudaLaunchKernelEx(&cfg, k_jacobi<128>, scratch_c, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info,
+                                            skip, lam_prev_c, jb.Wg, jb.flags, sub_c, m_keep, split, 0LL, 8);
+        if (ce != cudaSuccess) return TNML_CUDA_ERR(ce);
+      } else {
+        if (gram_done) cudaEventRecord(gram_done, st);
+        k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(scratch, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info, skip,
+                                                     lam_prev, jb.Wg, jb.flags, sub2, m_keep, split);
+      }
     } else {
       k_sum_partials<<<tnml_cdiv(NP * NP, 256), 256, 0, st>>>(partial, nparts, n, NP, jb.Wg, jb.flags, skip, pass_id,
                                                               sub2, 0);
@@ -1569,7 +1622,8 @@ static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
 
 // Shared implementation: X = R x C row-major matrix, rowmap/colmap = where row i / column j of the factors land.
 static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_rows, Idx3 rowmap, long long row_k,
-                    double* dst_cols, Idx3 colmap, long long col_k, double* svals, double* w, cudaStream_t st) {
+                    double* dst_cols, Idx3 colmap, long long col_k, double* svals, double* w, cudaStream_t st,
+                    cudaEvent_t gram_done = nullptr) {
   if (p.n > SVD_MAXN) return TNML_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1600,7 +1654,8 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   TNML_COUNT(1);
   k_gram<<<ggrid, 256, 0, st>>>(X, ss, sl, n, Nl, p.lc, partial, nullptr, nullptr);
   rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer, m,
-                     (int*)(w + p.off_sub) + 2);
+                     (int*)(w + p.off_sub) + 2, gram_done);
+  // (paths that do not launch the holding Cholesky never record the event: the caller created it in the recorded state)
   if (rc) return rc;
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
@@ -1636,13 +1691,14 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
 // small singular values, run off the critical path after a refine = 3 split; every kernel returns at once unless the
 // split set skip[1] = 0.  Only svals (the tail entries and the pass-2 sweep counter) are written.
 __global__ void __launch_bounds__(256) k_tail_svals(const double* __restrict__ lam2, const int* __restrict__ sub,
-                                                    const double* __restrict__ skip2, int n, double* __restrict__ svals) {
+                                                    const double* __restrict__ skip2, int n, double* __restrict__ svals,
+                                                    int compact) {
   if (*skip2 != 0.0) return;
-  const int k0 = sub[1];
-  for (int k = k0 + threadIdx.x; k < n; k += 256) svals[k] = sqrt(lam2[k]);
+  const int k0 = sub[1];   // compact: the single-CTA solver wrote the block's eigenvalues at lam2[0 .. ns)
+  for (int k = k0 + threadIdx.x; k < n; k += 256) svals[k] = sqrt(lam2[compact ? k - k0 : k]);
 }
 
-static int svd_tail(const double* X, SvdPlan p, double* svals, double* w, cudaStream_t st) {
+static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w, cudaStream_t st) {
   const int n = p.n, Nl = p.Nl;
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) return TNML_OK;                       // refine 3 never defers on the single-CTA path
@@ -1659,9 +1715,79 @@ static int svd_tail(const double* X, SvdPlan p, double* svals, double* w, cudaSt
   k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, w + p.off_vt1, nullptr, n, Y, Nl,
                                                                   dense, if_deferred);
   k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
+  // (Measured and rejected: solving the deferred block with the single-CTA kernel k_jacobi<64> instead of a second
+  // cluster -- the split on the critical path went from 0.91 to 1.39 ms; TNML_TAIL_SINGLE_CTA=1 re-enables it.)
+  static int single_cta = -1;
+  if (single_cta < 0) {
+    const char* e = getenv("TNML_TAIL_SINGLE_CTA");
+    single_cta = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  if (single_cta && m > 0 && n <= 128 && n - m <= 64) {
+    TNML_COUNT(1);
+    k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, p.nparts, n, vt2, lam2, 40, tol_final, 1, 3, svals + n + 1, skip2,
+                                              lam1, nullptr, nullptr, sub, 0, nullptr);
+    k_tail_svals<<<1, 256, 0, st>>>(lam2, sub, skip2, n, svals, 1);
+    return tnml_launch_status();
+  }
   int rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, 1, 3, svals + n + 1, skip2, lam1, jb, sub, st);
   if (rc) return rc;
-  k_tail_svals<<<1, 256, 0, st>>>(lam2, sub, skip2, n, svals);
+  k_tail_svals<<<1, 256, 0, st>>>(lam2, sub, skip2, n, svals, 0);
+  return tnml_launch_status();
+}
+
+// ---- deferred tail, batched -----------------------------------------------------------------------------------
+// Instead of solving the small block's eigenproblem after every split (a second cluster kernel per bond update, which
+// late in training -- when that block needs ~8 sweeps from scratch -- competes with the next split's cluster for a GPC
+// and stretched the critical path from 0.91 to 1.27 ms), the per-step tail call only RECORDS the block's Gram matrix;
+// tnml_svd_tail_batch solves all records of a sweep at once, one CTA each, when the history is read.
+// Record (doubles): [0] = {int ns, int k0}, [1] = skip flag, [2] = sweeps used, [3] = n, [8, 8+4096) Gram (ns x ns,
+// compact), [.., +4096) rotation scratch, [.., +64) eigenvalues.
+constexpr int TAIL_REC_GRAM = 8, TAIL_REC_VT = 8 + 4096, TAIL_REC_LAM = 8 + 8192, TAIL_REC_DOUBLES = 8 + 8192 + 64;
+
+__global__ void k_tail_record_hdr(double* __restrict__ rec, const int* __restrict__ sub, const double* __restrict__ skip2,
+                                  int n) {
+  if (threadIdx.x == 0) {
+    int* h = reinterpret_cast<int*>(rec);
+    const bool skip = *skip2 != 0.0 || sub[0] <= 0 || sub[0] > 64;
+    h[0] = skip ? 0 : sub[0];
+    h[1] = sub[1];
+    rec[1] = skip ? 1.0 : 0.0;
+    rec[2] = 0.0;
+    rec[3] = (double)n;
+  }
+}
+
+__global__ void k_tail_record_hdr_empty(double* __restrict__ rec) {
+  if (threadIdx.x == 0) { reinterpret_cast<int*>(rec)[0] = 0; reinterpret_cast<int*>(rec)[1] = 0; rec[1] = 1.0; }
+}
+
+__global__ void __launch_bounds__(64) k_tail_batch_svals(const double* __restrict__ recs, double* __restrict__ svals,
+                                                         long long svals_stride) {
+  const double* rec = recs + (size_t)blockIdx.x * TAIL_REC_DOUBLES;
+  if (rec[1] != 0.0) return;
+  const int* h = reinterpret_cast<const int*>(rec);
+  const int ns = h[0], k0 = h[1], n = (int)rec[3];
+  double* sv = svals + (size_t)blockIdx.x * svals_stride;
+  for (int i = threadIdx.x; i < ns; i += 64) sv[k0 + i] = sqrt(rec[TAIL_REC_LAM + i]);
+  if (threadIdx.x == 0) sv[n + 1] = rec[2];
+}
+
+static int svd_tail_record(const double* X, SvdPlan p, int m, double* rec, double* w, cudaStream_t st) {
+  const int n = p.n, Nl = p.Nl;
+  double *partial = w + p.off_partial, *Y = w + p.off_Y, *skip2 = w + p.off_skip + 1;
+  int* sub = (int*)(w + p.off_sub);
+  const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
+  const Idx3 dense{1, 1, 1, 0, 0};
+  const RowsAlt if_deferred{skip2, 0, nullptr, 0, 0, nullptr, nullptr};
+  const int tiles = tnml_cdiv(n, GRAM_TILE);
+  (void)m;
+  TNML_COUNT(4);
+  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, w + p.off_vt1, nullptr, n, Y, Nl,
+                                                                  dense, if_deferred);
+  k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
+  k_sum_partials<<<tnml_cdiv(64 * 64, 256), 256, 0, st>>>(partial, p.nparts, n, n, rec + TAIL_REC_GRAM,
+                                                          (int*)(w + p.off_flags), skip2, 3, sub, 1);
+  k_tail_record_hdr<<<1, 32, 0, st>>>(rec, sub, skip2, n);
   return tnml_launch_status();
 }
 }  // namespace tnml
@@ -1672,9 +1798,19 @@ extern "C" int64_t tnml_svd_split_workspace_bytes(int32_t Dl, int32_t Dr, int32_
   return (int64_t)svd_plan(Dl, Dr, L, left_dir).total * 8;
 }
 
+extern "C" int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl,
+                                 int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype,
+                                 tnml_stream_t stream, void* gram_done_event);
+
 extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl, int32_t Dr,
                               int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype,
                               tnml_stream_t stream) {
+  return tnml_svd_split_ev(Bnew, site_p, site_q, svals, ws, Dl, Dr, L, m, left_dir, refine, dtype, stream, nullptr);
+}
+
+extern "C" int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl,
+                                 int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype,
+                                 tnml_stream_t stream, void* gram_done_event) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(Bnew && site_p && site_q && svals && ws && Dl > 0 && Dr > 0 && L > 0);
   SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
@@ -1690,7 +1826,7 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
     colmap = Idx3{1, 1, 1, 0, 0}; col_k = 2LL * Dr;                                       // site_q[k][t][c]
   }
   return svd_core((const double*)Bnew, p, m, refine, (double*)site_p, rowmap, row_k, (double*)site_q, colmap, col_k,
-                  (double*)svals, (double*)ws, (cudaStream_t)stream);
+                  (double*)svals, (double*)ws, (cudaStream_t)stream, (cudaEvent_t)gram_done_event);
 }
 
 extern "C" int64_t tnml_svd_workspace_bytes(int32_t R, int32_t C) { return (int64_t)svd_plan_rc(R, C).total * 8; }
@@ -1707,9 +1843,34 @@ extern "C" int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* 
                   (double*)ws, (cudaStream_t)stream);
 }
 
-extern "C" int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, int32_t Dl, int32_t Dr, int32_t L,
-                                   int32_t left_dir, int32_t dtype, tnml_stream_t stream) {
+extern "C" int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, int32_t Dl, int32_t Dr,
+                                   int32_t L, int32_t m, int32_t left_dir, int32_t dtype, tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
-  TNML_REQUIRE(Bnew && svals && ws && Dl > 0 && Dr > 0 && L > 0);
-  return svd_tail((const double*)Bnew, svd_plan(Dl, Dr, L, left_dir), (double*)svals, (double*)ws, (cudaStream_t)stream);
+  TNML_REQUIRE(Bnew && svals && ws && Dl > 0 && Dr > 0 && L > 0 && m > 0);
+  const SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
+  const bool cluster = p.n > 128 || (p.n > 64 && jacobi_cluster_enabled());
+  if (record && cluster && p.n <= 128 && p.n - m <= 64)      // the deferred block has at most n - m <= 64 rows
+    return svd_tail_record((const double*)Bnew, p, m, (double*)record, (double*)ws, (cudaStream_t)stream);
+  if (record) {                                              // nothing recorded: mark the record as empty
+    k_tail_record_hdr_empty<<<1, 32, 0, (cudaStream_t)stream>>>((double*)record);
+  }
+  return svd_tail((const double*)Bnew, p, m, (double*)svals, (double*)ws, (cudaStream_t)stream);
+}
+
+/* Batched deferred tail: tnml_svd_split_tail with a record pointer only stores the small block's Gram matrix; this call
+ * solves `nrec` consecutive records (one CTA each) and writes the tail singular values into svals rows. */
+extern "C" int64_t tnml_svd_tail_record_bytes(void) { return (int64_t)TAIL_REC_DOUBLES * 8; }
+
+extern "C" int tnml_svd_tail_batch(void* recs, int32_t nrec, void* svals, int64_t svals_stride, int32_t dtype,
+                                   tnml_stream_t stream) {
+  TNML_F64_ONLY(dtype);
+  TNML_REQUIRE(recs && svals && nrec > 0 && svals_stride > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* r = (double*)recs;
+  TNML_COUNT(2);
+  k_jacobi<64><<<nrec, 256, 64 * 64 * 8, st>>>(r + TAIL_REC_GRAM, 1, 64, r + TAIL_REC_VT, r + TAIL_REC_LAM, 40,
+                                               8.0 * 2.220446049250313e-16, 1, 3, r + 2, r + 1, nullptr, nullptr, nullptr,
+                                               (const int*)r, 0, nullptr, (long long)TAIL_REC_DOUBLES);
+  k_tail_batch_svals<<<nrec, 64, 0, st>>>(r, (double*)svals, (long long)svals_stride);
+  return tnml_launch_status();
 }

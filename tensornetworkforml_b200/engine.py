@@ -123,12 +123,14 @@ class SweepEngine:
         self._side = None
         self._inflight = None
         # the second Jacobi pass that only refines the reported singular values of the DISCARDED tail runs on a third,
-        # normal-priority stream after the split (tnml_svd_split refine = 3 + tnml_svd_split_tail); two workspaces
-        # alternate so that the next split does not wait for it
+        # normal-priority stream after the split (tnml_svd_split refine = 3 + tnml_svd_split_tail); the workspaces
+        # rotate so that the following splits do not wait for it
         self.defer_tail = True
+        self._gram_evt = None
         self._ald_for = None          # (p, left_dir) whose activation / loss derivative was computed ahead (split_phase)
         self._tail = None
-        self._tail_evt = [None, None]
+        self.n_svd_ws = 4             # SVD workspaces in rotation: a tail refinement may lag this many splits - 1
+        self._tail_evt = [None] * self.n_svd_ws
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -377,14 +379,17 @@ class SweepEngine:
         # not be re-allocated in the middle of a sweep
         cap = self._dcap()
         nb = max(_lib.lib().tnml_svd_split_workspace_bytes(cap, cap, self.L, d) for d in (0, 1))
-        self._workspace("svd0", nb)
-        self._workspace("svd1", nb)
+        for i in range(self.n_svd_ws):
+            self._workspace("svd%d" % i, nb)
         self._workspace("gbuf", (cap * 4 * self.L * cap + 4) * 8)   # largest [dB | metrics] of the chain, never re-sized
         self._label_to("L" if left_dir else "R")
         if L2_flag:
             self._build_norm_stack(left_dir)
         nmax = 2 * max(self._dcap(), self.L) * 2
-        self.hist = dict(metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
+        rec_doubles = _lib.lib().tnml_svd_tail_record_bytes() // 8
+        self.hist = dict(tail_recs=torch.zeros((nsteps, rec_doubles), dtype=torch.float64, device=self.device),
+                         tail_solved=0,
+                         metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
                          stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
                          nsv=[], m=[], n=0)
@@ -480,7 +485,7 @@ class SweepEngine:
         new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
         new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
         defer = bool(self.defer_tail and self.svd_refine == 1 and side is not main)
-        par = step & 1
+        par = step % self.n_svd_ws
         ws_svd = self._workspace("svd%d" % par, _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
         f_out = self.f_buf[1 - self.f_cur]
         ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
@@ -492,12 +497,21 @@ class SweepEngine:
         with torch.cuda.stream(side):
             if self._tail_evt[par] is not None:
                 side.wait_event(self._tail_evt[par])    # this workspace's previous tail refinement has finished
+            gram_done = None
+            if side is not main:
+                if self._gram_evt is None:
+                    self._gram_evt = torch.cuda.Event()
+                    self._gram_evt.record(side)          # creates the CUDA event (in the recorded state)
+                gram_done = self._gram_evt
             with _Timed(self, "svd_split", 0.0):
-                call("tnml_svd_split", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
-                     3 if defer else self.svd_refine, F64, side.cuda_stream)
+                call("tnml_svd_split_ev", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
+                     3 if defer else self.svd_refine, F64, side.cuda_stream,
+                     gram_done.cuda_event if gram_done is not None else None)
             if defer:
                 split_done = torch.cuda.Event()
                 split_done.record(side)
+        if gram_done is not None:
+            main.wait_event(gram_done)      # the split's Cholesky cluster is placed before the projection fills the GPU
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
             # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
@@ -512,7 +526,11 @@ class SweepEngine:
                 Bn.record_stream(tail)
                 ws_svd.record_stream(tail)
                 self.hist["svals"].record_stream(tail)
-                call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), Dl, Dr, L, ldir, F64, tail.cuda_stream)
+                self.hist["tail_recs"].record_stream(tail)
+                # only the small block's Gram matrix is recorded here; history() solves all records of the sweep at once
+                rec_ptr = self.hist["tail_recs"].data_ptr() + step * self.hist["tail_recs"].shape[1] * 8
+                call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, Dl, Dr, L, m, ldir, F64,
+                     tail.cuda_stream)
                 evt = torch.cuda.Event()
                 evt.record(tail)
             self._tail_evt[par] = evt
@@ -552,6 +570,14 @@ class SweepEngine:
     def history(self):
         """Fetch the per-step record of the last sweep (one device->host copy)."""
         n = self.hist["n"]
+        if self._tail is not None and n > self.hist["tail_solved"]:
+            # the recorded small blocks of this sweep: one batched launch (one CTA per bond update) on the tail stream
+            k0 = self.hist["tail_solved"]
+            with torch.cuda.stream(self._tail):
+                call("tnml_svd_tail_batch", self.hist["tail_recs"].data_ptr() + k0 * self.hist["tail_recs"].shape[1] * 8,
+                     n - k0, self.hist["svals"].data_ptr() + k0 * self.hist["svals"].shape[1] * 8,
+                     self.hist["svals"].shape[1], F64, self._tail.cuda_stream)
+            self.hist["tail_solved"] = n
         self._join_tail()
         met = self.hist["metrics"][:n].cpu().numpy()
         stats = self.hist["stats"][:n].cpu().numpy()

@@ -257,7 +257,14 @@ def _run_svd(L, B, left_dir, m, refine=2, tail=False, before_tail=None):
     if tail:          # refine = 3: the deferred refinement of the discarded tail's singular values
         if before_tail is not None:
             before_tail.append((sv.cpu().numpy()[:n].copy(), site_p.cpu().numpy().copy(), site_q.cpu().numpy().copy()))
-        L.call("tnml_svd_split_tail", Bd.data_ptr(), sv.data_ptr(), ws.data_ptr(), Dl, Dr, nl, left_dir, L.F64, st())
+        if tail == "batch":   # record now, solve later (here: a batch of one)
+            rec = torch.zeros(L.lib().tnml_svd_tail_record_bytes() // 8, dtype=torch.float64, device="cuda")
+            L.call("tnml_svd_split_tail", Bd.data_ptr(), sv.data_ptr(), ws.data_ptr(), rec.data_ptr(), Dl, Dr, nl, m,
+                   left_dir, L.F64, st())
+            L.call("tnml_svd_tail_batch", rec.data_ptr(), 1, sv.data_ptr(), sv.numel(), L.F64, st())
+        else:
+            L.call("tnml_svd_split_tail", Bd.data_ptr(), sv.data_ptr(), ws.data_ptr(), None, Dl, Dr, nl, m, left_dir,
+                   L.F64, st())
     sp, sq = site_p.cpu().numpy(), site_q.cpu().numpy()
     if not left_dir:
         Ap, Aq = sp.reshape(Dl, 2, m), sq.reshape(m, 2, nl, Dr)
@@ -337,6 +344,10 @@ def test_svd_two_scale_spectrum_small_block_refinement(L, Dl, Dr, nl, left_dir):
     assert np.abs(sv3 - S).max() < 2e-13
     if 2 * min(Dl, Dr) > 64:                       # the cluster path defers; the single-CTA path never does
         assert np.abs(sv_before - S).max() > np.abs(sv3 - S).max()
+    # the same through the recorded / batched form of the tail
+    sv4, prod4, _, _ = _run_svd(L, B, left_dir, m, 3, tail="batch")
+    assert np.abs(prod4 - want).max() < 1e-11
+    assert np.abs(sv4 - S).max() < 2e-13
 
 
 def test_svd_rank_deficient(L):
