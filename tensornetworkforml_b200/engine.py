@@ -118,7 +118,7 @@ class SweepEngine:
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
-        self.project_ctas = int(os.environ.get("TNML_PROJECT_CTAS", "120"))   # grid cap of the projection while the SVD
+        self.project_ctas = int(os.environ.get("TNML_PROJECT_CTAS", "140"))   # grid cap of the projection while the SVD
                                                                           # split runs beside it (0 = no cap)
         self._side = None
         self._inflight = None
