@@ -237,10 +237,14 @@ def main():
     k0 = lib.tnml_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
     for _ in range(args.steps):
         device_step()
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     e1.record()
     barrier()
+    sweep_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(len(marks))]
     launches = lib.tnml_kernel_launches() - k0
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
@@ -350,6 +354,7 @@ def main():
                                      % world, l2_flush="inputs exceed L2 (env cache %.1f GB per GPU)" %
                                      (eng.env.numel() * eng.esz / 1e9), bond_updates_per_step=S - 1),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roofline, kernels=kern,
+                sweep_ms=sweep_ms, timed_kernel_pass_ms_per_step=ms_timed_pass / args.steps,
                 finite=finite, bonds_mid=eng.bond_dims()[S // 2], jacobi_sweeps=jacobi_sweeps, spectrum=spectrum)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = cpu_bond_updates(1, 3, Ns, D, L, c["lr"], c["wd"], c["act"], c["loss"])

@@ -67,3 +67,10 @@ extern "C" const char* tnml_error_string(int code) {
   if (code <= -1000) return cudaGetErrorString((cudaError_t)(-code - 1000));
   return "unknown error";
 }
+
+// Device-to-device copy on `stream` (per-step bookkeeping of the host engine without a framework call).
+extern "C" int tnml_copy(void* dst, const void* src, int64_t nbytes, tnml_stream_t stream) {
+  TNML_REQUIRE(dst && src && nbytes > 0);
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  return e == cudaSuccess ? TNML_OK : TNML_CUDA_ERR(e);
+}

@@ -127,6 +127,9 @@ class SweepEngine:
         # rotate so that the following splits do not wait for it
         self.defer_tail = True
         self._gram_evt = None
+        self._st = None
+        self._ws_cache = {}
+        self._split_evt = [None] * 4
         self._ald_for = None          # (p, left_dir) whose activation / loss derivative was computed ahead (split_phase)
         self._tail = None
         self.n_svd_ws = 4             # SVD workspaces in rotation: a tail refinement may lag this many splits - 1
@@ -134,7 +137,23 @@ class SweepEngine:
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        """Raw handle of the stream the current phase enqueues on (refreshed by _enter at every public entry point: a
+        torch.cuda.current_stream() lookup per kernel launch was a measurable part of the host time per bond update)."""
+        return self._st if self._st is not None else torch.cuda.current_stream(self.device).cuda_stream
+
+    def _enter(self):
+        main = torch.cuda.current_stream(self.device)
+        self._st = main.cuda_stream
+        return main
+
+    def _ws_bytes(self, name, *dims):
+        """Cached tnml_*_workspace_bytes query."""
+        key = (name,) + dims
+        v = self._ws_cache.get(key)
+        if v is None:
+            v = getattr(_lib.lib(), name)(*dims)
+            self._ws_cache[key] = v
+        return v
 
     def _host_register(self, arr):
         """Page-lock the NumPy buffer in place (process-wide registry in _lib, survives engine re-creation)."""
@@ -315,6 +334,7 @@ class SweepEngine:
     def forward(self):
         S, l = self.S, self.l_pos
         self._ald_for = None
+        self._enter()
         if l == 0:
             for p in range(S - 1, 0, -1):
                 self._advance_left(p)
@@ -328,6 +348,7 @@ class SweepEngine:
         call("tnml_site_predict", self._env(l), self._phi(l), self._weights(self.sites[l], "w32"), self._env(l + 1),
              _ptr(f), self.Ns, self.bonds[l], self.bonds[l + 1], self.L, self.DT, self._stream())
         self.f_cur = 0
+        self._st = None
         return f.view(self.Ns, self.L)
 
     # ------------------------------------------------------------------ sweep  (NC:384-436)
@@ -356,22 +377,24 @@ class SweepEngine:
             for p in range(0, S - 2):
                 self._norm_step(p, left_moving=False)
 
-    def _norm_step(self, p, left_moving):
+    def _norm_step(self, p, left_moving, st=None):
+        st = self._stream() if st is None else st
         Dl, Dr = self.bonds[p], self.bonds[p + 1]
         ws = self._workspace("nrm", 2 * Dl * Dr * 8)
         if left_moving:
             out = self._empty(Dl * Dl)
             call("tnml_norm_env_step", _ptr(self.nrmR[p + 1]), _ptr(self.sites[p]), _ptr(out), _ptr(ws), Dl, Dr, 1, F64,
-                 self._stream())
+                 st)
             self.nrmR[p] = out
         else:
             out = self._empty(Dr * Dr)
             call("tnml_norm_env_step", _ptr(self.nrmL[p]), _ptr(self.sites[p]), _ptr(out), _ptr(ws), Dl, Dr, 0, F64,
-                 self._stream())
+                 st)
             self.nrmL[p + 1] = out
 
     def begin_sweep(self, y, left_dir, L2_flag, nsteps=None):
         S = self.S
+        self._enter()
         self.set_labels(y)
         nsteps = S - 1 if nsteps is None else nsteps
         self._join_tail()                             # the previous record may still receive tail singular values
@@ -393,6 +416,7 @@ class SweepEngine:
                          stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
                          nsv=[], m=[], n=0)
+        self._st = None
 
     def sweep_step(self, lr, weight_dec, L2_flag, left_dir):
         """One bond update (NC:440-573 with update_B NC:577-763); everything stays on the device."""
@@ -401,7 +425,7 @@ class SweepEngine:
 
     def _act_lossder(self, p, q, met):
         """q, pp and the metric sums of the pair (p, q) from the current prediction f (NC:694-707)."""
-        ws = self._workspace("al", _lib.lib().tnml_act_lossder_workspace_bytes(self.Ns))
+        ws = self._workspace("al", self._ws_bytes("tnml_act_lossder_workspace_bytes", self.Ns))
         call("tnml_act_lossder", _ptr(self.f_buf[self.f_cur]), _ptr(self.y_dev), self._phi(p), self._phi(q),
              _ptr(self.q_buf), _ptr(self.pp_buf), _ptr(met), _ptr(ws), self.Ns, self.L, self.act, self.loss, self.T,
              self.DT, self._stream())
@@ -409,14 +433,14 @@ class SweepEngine:
     def update_phase(self, lr, weight_dec, L2_flag, left_dir, B_override=None):
         """update_B (NC:577-763): environment advance, loss derivative + metrics, gradient, regularisation, clipping,
         update.  Returns the context the split phase needs; ctx["Bn"] is the updated bond tensor B'."""
-        S, L, Ns, st = self.S, self.L, self.Ns, self._stream()
+        main = self._enter()
+        S, L, Ns, st = self.S, self.L, self.Ns, self._st
         l = self.l_pos
         p = l - 1 if left_dir else l
         q = p + 1
         if (not left_dir and not (0 <= l <= S - 2)) or (left_dir and not (1 <= l <= S - 1)):
             raise Exception("l = %d -> position not allowed for %s sweep step" % (l, "left" if left_dir else "right"))
         step = self.hist["n"]
-        main = torch.cuda.current_stream(self.device)
         side = self._side_stream() if self.overlap_svd else main
         Dl, Dm, Dr = self.bonds[p], self.bonds[q], self.bonds[q + 1]
         nB = Dl * 4 * L * Dr
@@ -425,15 +449,16 @@ class SweepEngine:
         #      norm-environment advance NC:1004-1061, B = A_p . A_q NC:484, L2 derivative E_L.B.E_R NC:1129-1135
         if side is not main:
             side.wait_stream(main)
-        with torch.cuda.stream(side):
+        if True:                                        # (explicit stream handles: no torch stream context needed)
             sst = side.cuda_stream
             if L2_flag:
                 if not left_dir and p > 0:
-                    self._norm_step(p - 1, left_moving=False)
+                    self._norm_step(p - 1, left_moving=False, st=sst)
                 if left_dir and q < S - 1:
-                    self._norm_step(q + 1, left_moving=True)
+                    self._norm_step(q + 1, left_moving=True, st=sst)
             if B_override is not None:
-                B.copy_(B_override.reshape(-1))
+                with torch.cuda.stream(side):
+                    B.copy_(B_override.reshape(-1))
             elif not left_dir:
                 call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
                      2 * Dr, 0.0, _ptr(B), 2 * Dr, F64, sst)
@@ -458,17 +483,17 @@ class SweepEngine:
         else:
             self._act_lossder(p, q, met)
         # gradient: K = Ns tensor-core reduction                                             NC:625-646, NC:710
-        ws = self._workspace("grad", _lib.lib().tnml_grad_workspace_bytes(Ns, Dl, Dr, L))
+        ws = self._workspace("grad", self._ws_bytes("tnml_grad_workspace_bytes", Ns, Dl, Dr, L))
         with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
             call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L,
                  self.DT, st)
         reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world,   # one collective per update
                                     count_written=True)
-        self.hist["metrics"][step].copy_(met)
+        call("tnml_copy", self.hist["metrics"].data_ptr() + step * 32, _ptr(met), 32, st)
         # regularisation, clipping, update                                                   NC:728-761
         if side is not main:
             main.wait_stream(side)                      # B and G are ready
-        ws = self._workspace("bu", _lib.lib().tnml_bond_update_workspace_bytes(Dl, Dr, L))
+        ws = self._workspace("bu", self._ws_bytes("tnml_bond_update_workspace_bytes", Dl, Dr, L))
         call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 6 * 8,
              _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec), 1 if L2_flag else 0, F64, st)
         self._inflight = (B, Bn, dB, G)
@@ -486,15 +511,16 @@ class SweepEngine:
         new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
         defer = bool(self.defer_tail and self.svd_refine == 1 and side is not main)
         par = step % self.n_svd_ws
-        ws_svd = self._workspace("svd%d" % par, _lib.lib().tnml_svd_split_workspace_bytes(Dl, Dr, L, 1 if left_dir else 0))
+        ws_svd = self._workspace("svd%d" % par, self._ws_bytes("tnml_svd_split_workspace_bytes", Dl, Dr, L,
+                                                               1 if left_dir else 0))
         f_out = self.f_buf[1 - self.f_cur]
-        ws = self._workspace("proj", _lib.lib().tnml_project_workspace_bytes(Ns, Dl, Dr, L))
+        ws = self._workspace("proj", self._ws_bytes("tnml_project_workspace_bytes", Ns, Dl, Dr, L))
         if side is not main:
             side.wait_stream(main)                      # B' is ready
         sv_ptr = self.hist["svals"].data_ptr() + step * self.hist["svals"].shape[1] * 8
         ldir = 1 if left_dir else 0
         # the SVD is issued first: its kernels are short or small and should get SMs before the projection fills the GPU
-        with torch.cuda.stream(side):
+        if True:
             if self._tail_evt[par] is not None:
                 side.wait_event(self._tail_evt[par])    # this workspace's previous tail refinement has finished
             gram_done = None
@@ -508,7 +534,9 @@ class SweepEngine:
                      3 if defer else self.svd_refine, F64, side.cuda_stream,
                      gram_done.cuda_event if gram_done is not None else None)
             if defer:
-                split_done = torch.cuda.Event()
+                split_done = self._split_evt[par]
+                if split_done is None:
+                    split_done = self._split_evt[par] = torch.cuda.Event()
                 split_done.record(side)
         if gram_done is not None:
             main.wait_event(gram_done)      # the split's Cholesky cluster is placed before the projection fills the GPU
@@ -520,7 +548,7 @@ class SweepEngine:
         if defer:
             tail = self._tail_stream()
             tail.wait_event(split_done)
-            with torch.cuda.stream(tail):
+            if True:
                 # these three are used by the tail stream after the main stream is done with them: tell the allocator, so
                 # that dropping the engine (or re-sizing a workspace) cannot hand their memory out while a tail is pending
                 Bn.record_stream(tail)
@@ -531,7 +559,9 @@ class SweepEngine:
                 rec_ptr = self.hist["tail_recs"].data_ptr() + step * self.hist["tail_recs"].shape[1] * 8
                 call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, Dl, Dr, L, m, ldir, F64,
                      tail.cuda_stream)
-                evt = torch.cuda.Event()
+                evt = self._tail_evt[par]
+                if evt is None:
+                    evt = torch.cuda.Event()
                 evt.record(tail)
             self._tail_evt[par] = evt
         self.f_cur = 1 - self.f_cur
@@ -558,6 +588,7 @@ class SweepEngine:
         self.hist["nsv"].append(min(R, Cc))
         self.hist["m"].append(m)
         self.hist["n"] = step + 1
+        self._st = None
         return f_out.view(Ns, L)
 
     def sweep(self, y, lr, weight_dec, L2_flag=True, left_dir=False):
