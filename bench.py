@@ -117,6 +117,8 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix=".csv")
         self.proc = None
+        if gpu_index is None:
+            return
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
@@ -233,7 +235,8 @@ def main():
     for _ in range(args.warmup):
         device_step()
     barrier()
-    clocks = ClockSampler(local_rank)
+    # one sampler (rank 0's GPU) is enough: eight 10 Hz nvidia-smi pollers measurably slowed the 8-rank run
+    clocks = ClockSampler(local_rank if rank == 0 else None)
     k0 = lib.tnml_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -59,6 +59,10 @@ const char* tnml_error_string(int code);
 /* Asynchronous device-to-device copy of nbytes on `stream`. */
 int tnml_copy(void* dst, const void* src, int64_t nbytes, tnml_stream_t stream);
 
+/* A one-thread kernel that idles for about `ns` nanoseconds (at most 100 us) on `stream`: lets a caller make a kernel on
+ * one stream eligible slightly after a kernel on another (see tnml_svd_split_ev). */
+int tnml_delay(int64_t ns, tnml_stream_t stream);
+
 /* Page-lock a caller-owned HOST buffer in place (and release it), so the host->device copy of the input batch is a
  * direct DMA transfer instead of a staged one.  Returns 0 (registered now), 1 (was already registered) or < 0. */
 int tnml_host_register(void* host_ptr, uint64_t bytes);

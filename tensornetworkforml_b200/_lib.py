@@ -21,6 +21,7 @@ SIGNATURES = {
     "tnml_kernel_launches": (C.c_uint64, []),
     "tnml_error_string": (C.c_char_p, [C.c_int]),
     "tnml_copy": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "tnml_delay": (C.c_int, [_i64, _vp]),
     "tnml_host_register": (C.c_int, [_vp, C.c_uint64]),
     "tnml_host_unregister": (C.c_int, [_vp]),
     "tnml_feature_map": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),

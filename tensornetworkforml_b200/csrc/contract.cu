@@ -74,3 +74,22 @@ extern "C" int tnml_copy(void* dst, const void* src, int64_t nbytes, tnml_stream
   cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
   return e == cudaSuccess ? TNML_OK : TNML_CUDA_ERR(e);
 }
+
+// One thread idles for ~ns nanoseconds (bounded): the host engine uses it to make the projection eligible a few
+// microseconds AFTER the SVD split's SM-holding Cholesky cluster, so that the cluster's CTAs are placed first.
+__global__ void k_delay(unsigned long long ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (ns > 100000ull) ns = 100000ull;
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < ns);
+}
+
+extern "C" int tnml_delay(int64_t ns, tnml_stream_t stream) {
+  TNML_REQUIRE(ns >= 0);
+  TNML_COUNT(1);
+  k_delay<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)ns);
+  return tnml_launch_status();
+}

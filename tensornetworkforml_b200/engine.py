@@ -58,18 +58,20 @@ def choose_m(rule, max_bond, left_dir, l_pos, S, Dl, R, C):
 class _Timed:
     """Optional CUDA-event bracket around one C-ABI call (bench.py's live per-kernel timing)."""
 
-    def __init__(self, eng, name, flops):
-        self.eng, self.name, self.flops = eng, name, flops
+    def __init__(self, eng, name, flops, stream=None):
+        self.eng, self.name, self.flops, self.stream = eng, name, flops, stream
 
     def __enter__(self):
         if self.eng.timers is not None:
+            if self.stream is None:
+                self.stream = torch.cuda.current_stream(self.eng.device)
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
-            self.e0.record(torch.cuda.current_stream(self.eng.device))
+            self.e0.record(self.stream)
 
     def __exit__(self, *exc):
         if self.eng.timers is not None:
-            self.e1.record(torch.cuda.current_stream(self.eng.device))
+            self.e1.record(self.stream)
             self.eng.timers.setdefault(self.name, []).append((self.e0, self.e1, self.flops))
         return False
 
@@ -127,6 +129,7 @@ class SweepEngine:
         # rotate so that the following splits do not wait for it
         self.defer_tail = True
         self._gram_evt = None
+        self.project_delay_ns = int(os.environ.get("TNML_PROJECT_DELAY_NS", "10000"))
         self._st = None
         self._ws_cache = {}
         self._split_evt = [None] * 4
@@ -529,7 +532,7 @@ class SweepEngine:
                     self._gram_evt = torch.cuda.Event()
                     self._gram_evt.record(side)          # creates the CUDA event (in the recorded state)
                 gram_done = self._gram_evt
-            with _Timed(self, "svd_split", 0.0):
+            with _Timed(self, "svd_split", 0.0, side):
                 call("tnml_svd_split_ev", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
                      3 if defer else self.svd_refine, F64, side.cuda_stream,
                      gram_done.cuda_event if gram_done is not None else None)
@@ -539,7 +542,11 @@ class SweepEngine:
                     split_done = self._split_evt[par] = torch.cuda.Event()
                 split_done.record(side)
         if gram_done is not None:
-            main.wait_event(gram_done)      # the split's Cholesky cluster is placed before the projection fills the GPU
+            # the split's SM-holding Cholesky cluster must be placed before the projection fills the GPU: the projection
+            # becomes eligible a few microseconds after the event (without the pause the order was a race that the
+            # first process on a fresh box lost: 454 instead of 345 ms per sweep)
+            main.wait_event(gram_done)
+            call("tnml_delay", self.project_delay_ns, st)
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
             # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
