@@ -1660,13 +1660,11 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   if (refine) {
     const Idx3 dense{1, 1, 1, 0, 0};
     TNML_COUNT(4);
-    const RowsAlt none{nullptr, -1, nullptr, 0, 0, nullptr, nullptr};
     // Y is only needed when the second pass runs on this path (skip1 == nullptr: always)
     const RowsAlt only_if_pass2{skip1, skip1 ? 0 : -1, nullptr, 0, 0, nullptr, nullptr};
     const RowsAlt first_pass_if_skipped{skip1, skip1 ? 2 : -1, X, ss, sl, vt1, lam1};
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, vt1, nullptr, n, Y, Nl, dense,
                                                                     only_if_pass2);
-    (void)none;
     k_gram<<<ggrid, 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip1, sub);
     rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, sub ? 1 : 0, 2, svals + n + 1, skip1, lam1, jb, sub,
                        st);

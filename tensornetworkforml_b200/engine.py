@@ -452,26 +452,25 @@ class SweepEngine:
         #      norm-environment advance NC:1004-1061, B = A_p . A_q NC:484, L2 derivative E_L.B.E_R NC:1129-1135
         if side is not main:
             side.wait_stream(main)
-        if True:                                        # (explicit stream handles: no torch stream context needed)
-            sst = side.cuda_stream
-            if L2_flag:
-                if not left_dir and p > 0:
-                    self._norm_step(p - 1, left_moving=False, st=sst)
-                if left_dir and q < S - 1:
-                    self._norm_step(q + 1, left_moving=True, st=sst)
-            if B_override is not None:
-                with torch.cuda.stream(side):
-                    B.copy_(B_override.reshape(-1))
-            elif not left_dir:
-                call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
-                     2 * Dr, 0.0, _ptr(B), 2 * Dr, F64, sst)
-            else:
-                call("tnml_gemm", 0, 0, Dl * 2, L * 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
-                     L * 2 * Dr, 0.0, _ptr(B), L * 2 * Dr, F64, sst)
-            if L2_flag:
-                ws_l2 = self._workspace("l2", nB * 8)
-                call("tnml_l2_term", _ptr(B), _ptr(self.nrmL[p]), _ptr(self.nrmR[q + 1]), _ptr(G), _ptr(ws_l2), Dl, Dr, L,
-                     F64, sst)
+        sst = side.cuda_stream                          # explicit stream handles: no torch stream context needed
+        if L2_flag:
+            if not left_dir and p > 0:
+                self._norm_step(p - 1, left_moving=False, st=sst)
+            if left_dir and q < S - 1:
+                self._norm_step(q + 1, left_moving=True, st=sst)
+        if B_override is not None:
+            with torch.cuda.stream(side):
+                B.copy_(B_override.reshape(-1))
+        elif not left_dir:
+            call("tnml_gemm", 0, 0, Dl * 2 * L, 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
+                 2 * Dr, 0.0, _ptr(B), 2 * Dr, F64, sst)
+        else:
+            call("tnml_gemm", 0, 0, Dl * 2, L * 2 * Dr, Dm, 1.0, _ptr(self.sites[p]), Dm, _ptr(self.sites[q]),
+                 L * 2 * Dr, 0.0, _ptr(B), L * 2 * Dr, F64, sst)
+        if L2_flag:
+            ws_l2 = self._workspace("l2", nB * 8)
+            call("tnml_l2_term", _ptr(B), _ptr(self.nrmL[p]), _ptr(self.nrmR[q + 1]), _ptr(G), _ptr(ws_l2), Dl, Dr, L,
+                 F64, sst)
         # ---- critical path on the main stream
         # environment advance over the site fixed by the previous step                       NC:637-642 / NC:669-674
         if not left_dir and p > 0:
@@ -523,24 +522,23 @@ class SweepEngine:
         sv_ptr = self.hist["svals"].data_ptr() + step * self.hist["svals"].shape[1] * 8
         ldir = 1 if left_dir else 0
         # the SVD is issued first: its kernels are short or small and should get SMs before the projection fills the GPU
-        if True:
-            if self._tail_evt[par] is not None:
-                side.wait_event(self._tail_evt[par])    # this workspace's previous tail refinement has finished
-            gram_done = None
-            if side is not main:
-                if self._gram_evt is None:
-                    self._gram_evt = torch.cuda.Event()
-                    self._gram_evt.record(side)          # creates the CUDA event (in the recorded state)
-                gram_done = self._gram_evt
-            with _Timed(self, "svd_split", 0.0, side):
-                call("tnml_svd_split_ev", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
-                     3 if defer else self.svd_refine, F64, side.cuda_stream,
-                     gram_done.cuda_event if gram_done is not None else None)
-            if defer:
-                split_done = self._split_evt[par]
-                if split_done is None:
-                    split_done = self._split_evt[par] = torch.cuda.Event()
-                split_done.record(side)
+        if self._tail_evt[par] is not None:
+            side.wait_event(self._tail_evt[par])        # this workspace's previous tail refinement has finished
+        gram_done = None
+        if side is not main:
+            if self._gram_evt is None:
+                self._gram_evt = torch.cuda.Event()
+                self._gram_evt.record(side)              # creates the CUDA event (in the recorded state)
+            gram_done = self._gram_evt
+        with _Timed(self, "svd_split", 0.0, side):
+            call("tnml_svd_split_ev", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
+                 3 if defer else self.svd_refine, F64, side.cuda_stream,
+                 gram_done.cuda_event if gram_done is not None else None)
+        if defer:
+            split_done = self._split_evt[par]
+            if split_done is None:
+                split_done = self._split_evt[par] = torch.cuda.Event()
+            split_done.record(side)
         if gram_done is not None:
             # the split's SM-holding Cholesky cluster must be placed before the projection fills the GPU: the projection
             # becomes eligible a few microseconds after the event (without the pause the order was a race that the
@@ -548,40 +546,35 @@ class SweepEngine:
             main.wait_event(gram_done)
             call("tnml_delay", self.project_delay_ns, st)
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
-            # beside a cluster-parallel SVD the projection leaves ~1/4 of the SMs (whole GPCs) free: measured optimum
+            # beside a cluster-parallel SVD the projection leaves the 8 SMs of the split's cluster free
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
                  Dl, Dr, L, cap, self.DT, st)
         if defer:
             tail = self._tail_stream()
             tail.wait_event(split_done)
-            if True:
-                # these three are used by the tail stream after the main stream is done with them: tell the allocator, so
-                # that dropping the engine (or re-sizing a workspace) cannot hand their memory out while a tail is pending
-                Bn.record_stream(tail)
-                ws_svd.record_stream(tail)
-                self.hist["svals"].record_stream(tail)
-                self.hist["tail_recs"].record_stream(tail)
-                # only the small block's Gram matrix is recorded here; history() solves all records of the sweep at once
-                rec_ptr = self.hist["tail_recs"].data_ptr() + step * self.hist["tail_recs"].shape[1] * 8
-                call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, Dl, Dr, L, m, ldir, F64,
-                     tail.cuda_stream)
-                evt = self._tail_evt[par]
-                if evt is None:
-                    evt = torch.cuda.Event()
-                evt.record(tail)
+            # these are used by the tail stream after the main stream is done with them: tell the allocator, so that
+            # dropping the engine (or re-sizing a workspace) cannot hand their memory out while a tail is pending
+            Bn.record_stream(tail)
+            ws_svd.record_stream(tail)
+            self.hist["svals"].record_stream(tail)
+            self.hist["tail_recs"].record_stream(tail)
+            # only the small block's Gram matrix is recorded here; history() solves all records of the sweep at once
+            rec_ptr = self.hist["tail_recs"].data_ptr() + step * self.hist["tail_recs"].shape[1] * 8
+            call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, Dl, Dr, L, m, ldir, F64,
+                 tail.cuda_stream)
+            evt = self._tail_evt[par]
+            if evt is None:
+                evt = torch.cuda.Event()
+            evt.record(tail)
             self._tail_evt[par] = evt
         self.f_cur = 1 - self.f_cur
         # the next bond update's activation / loss derivative / metrics only need the new prediction: enqueue them now,
         # so that they run while the SVD split is still busy on the side stream
         pn = p - 1 if left_dir else p + 1
         if side is not main and 0 <= pn and pn + 1 <= S - 1:
-            Dln = self.bonds[pn] if not left_dir else self.bonds[pn]
-            Drn = self.bonds[pn + 2]
-            if not left_dir:
-                Dln = m                                  # the bond between p and q has just been set to m
-            else:
-                Drn = m
+            # bonds of the next pair (pn, pn + 1); the bond between p and q is about to be set to m
+            Dln, Drn = (m, self.bonds[pn + 2]) if not left_dir else (self.bonds[pn], m)
             nBn = Dln * 4 * L * Drn
             gb = self._workspace("gbuf", (nBn + 4) * 8)
             self._act_lossder(pn, pn + 1, gb[nBn:nBn + 4])
