@@ -136,3 +136,31 @@ def test_shipped_reference_pickle_loads_into_our_classes():
         net = pickle.load(fh)
     assert isinstance(net, tn.Network) and net.N == 64 and net.L == 2 and net.l_pos == 63
     assert len(net.As) == 64 and isinstance(net.As[0], tn.Tensor)
+
+
+def test_reduce_gradient_with_count_written_by_the_kernel():
+    """tnml_act_lossder writes [n_correct, sum|y-f|, count, 0] itself; the host must then leave the extras alone."""
+    import torch
+    from tensornetworkforml_b200.parallel import N_EXTRA, reduce_gradient_and_metrics
+    n = 5
+    buf = torch.arange(n + N_EXTRA, dtype=torch.float64)
+    buf[n + 2], buf[n + 3] = 123.0, 0.0                       # what the kernel wrote
+    out = reduce_gradient_and_metrics(buf.clone(), n, 999, world=1, count_written=True)
+    assert torch.equal(out, buf)
+    out = reduce_gradient_and_metrics(buf.clone(), n, 999, world=1)            # legacy path: host fills count / spare
+    assert out[n + 2] == 999.0 and out[n + 3] == 0.0 and torch.equal(out[:n + 2], buf[:n + 2])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times) prints one JSON line with the contract's keys; it
+    needs no GPU.  Two bond updates at the full Ns = 60000 on the host cores."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "bond_updates_per_s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["unit"] == "bond-updates/s" and line["config"]["Ns"] == 60000
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
