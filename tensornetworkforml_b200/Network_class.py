@@ -292,6 +292,7 @@ class Network():
         ctx = eng.update_phase(lr, weight_dec, L2_flag, left_dir,
                                B_override=torch.from_numpy(Bc).to(eng.device))
         torch.cuda.current_stream(eng.device).wait_stream(ctx["side"])
+        eng._st = None                       # update_phase without split_phase: drop the cached stream handle
         eng.hist["n"] = 1
         eng.hist["nsv"], eng.hist["m"] = [0], [0]
         h = eng.history()
