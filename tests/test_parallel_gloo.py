@@ -32,7 +32,7 @@ def _problem():
     return Ns, L, Le, Re, pa, pb, f, y
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, count_written=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     Ns, L, Le, Re, pa, pb, f, y = _problem()
@@ -47,17 +47,22 @@ def _worker(rank, world, port, out):
     buf[n] = float((np.argmax(fa, 1) == y[lo:hi]).sum())
     buf[n + 1] = float(np.abs(y1h - fa).sum())
     buf[n + P.N_EXTRA:] = 7.0                                   # bytes past the payload must not be touched
-    P.reduce_gradient_and_metrics(buf, n, hi - lo, world=world)
+    if count_written:                                           # what tnml_act_lossder writes on the device
+        buf[n + 2], buf[n + 3] = float(hi - lo), 0.0
+        P.reduce_gradient_and_metrics(buf, n, -1, world=world, count_written=True)
+    else:
+        P.reduce_gradient_and_metrics(buf, n, hi - lo, world=world)
     fmax = P.global_abs_max(np.abs(f[lo:hi]).max(), "cpu", world=world)
     out[rank] = (buf.numpy().copy(), fmax, (lo, hi))
     dist.destroy_process_group()
 
 
-def test_sharded_sums_equal_single_process_sums():
+@pytest.mark.parametrize("count_written", [False, True])
+def test_sharded_sums_equal_single_process_sums(count_written):
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, count_written), nprocs=world, join=True)
     Ns, L, Le, Re, pa, pb, f, y = _problem()
     y1h = np.eye(L)[y]
     g = O.loss_derivative(f, y1h, "linear", "MSE", 0.1)
