@@ -419,6 +419,7 @@ class SweepEngine:
                          stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
                          nsv=[], m=[], n=0)
+        self.hist["tail_recs"][:, 1] = 1.0            # "nothing recorded" until a tail call writes the header
         self._st = None
 
     def sweep_step(self, lr, weight_dec, L2_flag, left_dir):
