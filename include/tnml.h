@@ -184,6 +184,21 @@ int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals,
  * singular values into svals + i * svals_stride (doubles) for record i.  Same Dl, Dr, L, m, left_dir as the split. */
 int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, int32_t Dl, int32_t Dr, int32_t L,
                         int32_t m, int32_t left_dir, int32_t dtype, tnml_stream_t stream);
+/* Warm-started split (the replacement of np.linalg.svd at NC:887 for a bond that is visited again and again by the
+ * sweeps of a training run).  `warm` is a per-(bond, direction) device buffer of tnml_svd_warm_bytes() bytes, zeroed by
+ * the caller before its first use and owned by the caller between calls: every split leaves its short-side rotation
+ * there.  fast != 0 (2 Dl = 2 Dr = 128 or the mirrored left-sweep shape, m = 64, refine = 3): the split first tries the
+ * deflation path -- one subspace-iteration step from the previous visit's m dominant vectors, CholeskyQR, Rayleigh-Ritz
+ * on the 64 x 64 projected Gram matrix (two-sided Jacobi in one CTA), a-posteriori residual / gap / conditioning
+ * gates on the device -- and runs the ordinary pipeline (single-CTA form) only when a gate fails.  Results agree with
+ * the cold split to rounding.  fast = 0 or warm = NULL: exactly tnml_svd_split_ev (plus the rotation left in `warm`).
+ * The tail call must receive the same warm / fast arguments. */
+int64_t tnml_svd_warm_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
+int tnml_svd_split_warm(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, void* warm, int32_t Dl,
+                        int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t fast, int32_t dtype,
+                        tnml_stream_t stream, void* gram_done_event);
+int tnml_svd_split_tail_warm(const void* Bnew, void* svals, void* ws, void* record, void* warm, int32_t Dl, int32_t Dr,
+                             int32_t L, int32_t m, int32_t left_dir, int32_t fast, int32_t dtype, tnml_stream_t stream);
 int64_t tnml_svd_tail_record_bytes(void);
 int tnml_svd_tail_batch(void* recs, int32_t nrec, void* svals, int64_t svals_stride, int32_t dtype, tnml_stream_t stream);
 

@@ -46,6 +46,10 @@ SIGNATURES = {
     "tnml_svd_split": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_svd_split_ev": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "tnml_svd_split_tail": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "tnml_svd_warm_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "tnml_svd_split_warm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp,
+                                      _vp]),
+    "tnml_svd_split_tail_warm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "tnml_svd_tail_record_bytes": (_i64, []),
     "tnml_svd_tail_batch": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp]),
     "tnml_svd_workspace_bytes": (_i64, [_i32, _i32]),

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "tnml.h"
 
 #define TNML_CUDA_ERR(e) (-(1000 + (int)(e)))
@@ -29,12 +31,36 @@ static inline int tnml_launch_status() {
     if ((dtype) != TNML_F64) return TNML_ERR_INVALID;     \
   } while (0)
 
+// Function attributes (dynamic shared memory opt-in, non-portable cluster size) are PER DEVICE: every launcher keeps one
+// DeviceOnce and sets its attributes the first time it runs on each device.  Two host threads racing through the same
+// launcher both set the (idempotent) attributes; the bit is published only afterwards.
+static inline int tnml_current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool needed(int dev) const { return !((done.load(std::memory_order_acquire) >> dev) & 1ULL); }
+  void mark(int dev) { done.fetch_or(1ULL << dev, std::memory_order_release); }
+};
+// SM count of the current device (148 on B200), queried once per device.
+static inline int tnml_num_sms() {
+  static std::atomic<int> cache[64];
+  const int d = tnml_current_device();
+  int v = cache[d].load(std::memory_order_relaxed);
+  if (v <= 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+    cache[d].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static inline int64_t tnml_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int tnml_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 namespace tnml {
 
-constexpr int kNumSMs = 148;  // B200
 
 // ---- FP64 tensor-core MMA (SASS DMMA.8x8x4) ----------------------------------------------------------
 // A 8x4 row-major : lane holds A[lane>>2][lane&3]

@@ -864,11 +864,15 @@ int env_advance(const float* E, const float* phi, const float* W, float* out, in
   rc = make_tensor_map_f32(&mapW, W, (uint64_t)2 * M, (uint64_t)K, (uint64_t)K, (uint32_t)mcs);
   if (rc) return rc;
   const size_t smem = (size_t)(2 * mcs / 32) * K * ROW_BYTES + (size_t)(K / 32) * 128 * ROW_BYTES + 1024;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_env_advance_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the largest request of this launcher (K = 256, where mcs = 32), opted in once per device
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (attr_once.needed(attr_dev)) {
+    const size_t smem_max = (size_t)(2 * 32 / 32) * 256 * ROW_BYTES + (size_t)(256 / 32) * 128 * ROW_BYTES + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_env_advance_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem_max > smem ? smem_max : smem));
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    smem_set = smem;
+    attr_once.mark(attr_dev);
   }
   dim3 grid(tnml_cdiv(Ns, 128), M / mcs);
   k_env_advance_tc<<<grid, 128, smem, st>>>(mapE, mapW, (const float2*)phi, out, Ns, K, M, mcs);
@@ -905,7 +909,7 @@ static GradPlan grad_plan(int64_t Ns, int Dl, int Dr, int L) {
     p.a_chunks = Dl / 64;
     p.c_chunks = Dr / 64;
     p.cols = p.ngroups * p.a_chunks * p.c_chunks;
-    int k = kNumSMs / p.cols;
+    int k = tnml_num_sms() / p.cols;
     const int kmax = tnml_cdiv(Ns, 4 * GT_KB);
     if (k > kmax) k = kmax;
     if (k < 1) k = 1;
@@ -916,7 +920,7 @@ static GradPlan grad_plan(int64_t Ns, int Dl, int Dr, int L) {
     p.a_chunks = tnml_cdiv(Dl, 8);
     p.c_chunks = tnml_cdiv(Dr, 32);
     p.cols = p.a_chunks * p.c_chunks;
-    int k = 2 * kNumSMs / p.cols;
+    int k = 2 * tnml_num_sms() / p.cols;
     const int kmax = tnml_cdiv(Ns, 256);
     if (k > kmax) k = kmax;
     if (k < 1) k = 1;
@@ -939,11 +943,12 @@ int grad(const float* g, const float* pp, const float* Lenv, const float* Renv, 
   const int64_t nB = (int64_t)Dl * 4 * L * Dr;
   TNML_COUNT(2);
   if (p.tc) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    const int attr_dev = tnml_current_device();
+    if (attr_once.needed(attr_dev)) {
       cudaError_t e = cudaFuncSetAttribute(k_grad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM_BYTES);
       if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-      attr_set = true;
+      attr_once.mark(attr_dev);
     }
     k_grad_tc<<<dim3(p.cols, p.ks), GT_THREADS, GT_SMEM_BYTES, st>>>(g, pp, Lenv, Renv, (float*)ws, Ns, Dl, Dr, L,
                                                                       p.ngroups, p.a_chunks, p.c_chunks, p.chunk);
@@ -973,11 +978,12 @@ int project(const double* B, const float* pp, const float* Lenv, const float* Re
     k_project_simt<<<tnml_cdiv(Ns, 32), 256, 0, st>>>(Bf, pp, Lenv, Renv, f, Ns, Dl, Dr, L);
     return tnml_launch_status();
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (attr_once.needed(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(k_project_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PJ_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   const int a_chunks = Dl / 64, c_chunks = Dr / 64, ngroups = tnml_cdiv(L, PJ_NL);
   float* fpart = (float*)((char*)ws + tnml_align_up(nB * 4, 1024));
@@ -989,7 +995,7 @@ int project(const double* B, const float* pp, const float* Lenv, const float* Re
   rc = make_tensor_map_f32(&mapB, Bf, (uint64_t)L * c_chunks * a_chunks * 256, 64, 64, 256);
   if (rc) return rc;
   const int cols = ngroups * c_chunks;
-  const int budget = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+  const int budget = (max_ctas > 0 && max_ctas < tnml_num_sms()) ? max_ctas : tnml_num_sms();
   const int ntiles = tnml_cdiv(Ns, 128);
   int k = budget / cols;
   if (k < 1) k = 1;

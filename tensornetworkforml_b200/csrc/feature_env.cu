@@ -325,19 +325,21 @@ extern "C" int tnml_env_advance(const void* E, const void* phi_p, const void* W,
     return f32::env_advance((const float*)E, (const float*)phi_p, (const float*)W, (float*)out, Ns, K, M,
                             (cudaStream_t)stream);
   TNML_COUNT(1);
-  static int use_tma = -1;                   // TNML_ENV_TMA=0: always the plain kernel (A/B knob)
-  if (use_tma < 0) {
+  static const int use_tma = [] {            // TNML_ENV_TMA=0: always the plain kernel (A/B knob)
     const char* ev = getenv("TNML_ENV_TMA");
-    use_tma = (ev && atoi(ev) == 0) ? 0 : 1;
-    if (use_tma) {
-      cudaError_t e = cudaFuncSetAttribute(k_env_advance_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_BYTES);
-      if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    }
+    return (ev && atoi(ev) == 0) ? 0 : 1;
+  }();
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (use_tma && attr_once.needed(attr_dev)) {
+    cudaError_t e = cudaFuncSetAttribute(k_env_advance_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, EB_SMEM_BYTES);
+    if (e != cudaSuccess) return TNML_CUDA_ERR(e);
+    attr_once.mark(attr_dev);
   }
   if (use_tma && K <= 64 && M <= 64 && K % 4 == 0 && M % 2 == 0 && Ns >= 4 * EB_BM &&
       (((uintptr_t)E | (uintptr_t)W | (uintptr_t)out) & 15) == 0) {
     const int ntiles = tnml_cdiv(Ns, EB_BM);
-    k_env_advance_tma<<<ntiles < kNumSMs ? ntiles : kNumSMs, 256, EB_SMEM_BYTES, (cudaStream_t)stream>>>(
+    k_env_advance_tma<<<ntiles < tnml_num_sms() ? ntiles : tnml_num_sms(), 256, EB_SMEM_BYTES, (cudaStream_t)stream>>>(
         (const double*)E, (const double2*)phi_p, (const double*)W, (double*)out, Ns, K, M);
     return tnml_launch_status();
   }

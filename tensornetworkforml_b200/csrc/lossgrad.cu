@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_grad_reduce(const double* __restrict__ 
 static void grad_plan(int64_t Ns, int Dl, int Dr, int L, int* cols, int* ks, int64_t* chunk) {
   int a_chunks = tnml_cdiv(Dl, 64), c_chunks = tnml_cdiv(Dr, 64);
   *cols = L * a_chunks * c_chunks;
-  int k = kNumSMs / *cols;
+  int k = tnml_num_sms() / *cols;
   int kmax = tnml_cdiv(Ns, 4 * GR_BK);
   if (k > kmax) k = kmax;
   if (k < 1) k = 1;
@@ -320,13 +320,14 @@ extern "C" int tnml_grad(const void* q, const void* Lenv, const void* Renv, void
     return f32::grad(g, g + ((Ns * L + 3) & ~(int64_t)3), (const float*)Lenv, (const float*)Renv, (double*)dB, ws, Ns,
                      Dl, Dr, L, (cudaStream_t)stream);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (attr_once.needed(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(k_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     e = cudaFuncSetAttribute(k_grad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GR_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   int cols, ks;
   int64_t chunk;

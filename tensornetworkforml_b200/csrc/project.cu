@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_fpart_reduce(const double* __restrict__
 static void project_plan(int64_t Ns, int Dr, int L, int max_ctas, int* cols, int* ks, int64_t* chunk) {
   int c_chunks = tnml_cdiv(Dr, 64);
   *cols = L * c_chunks;
-  const int budget = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+  const int budget = (max_ctas > 0 && max_ctas < tnml_num_sms()) ? max_ctas : tnml_num_sms();
   int k = budget / *cols;
   int kmax = tnml_cdiv(Ns, 2 * PJ_BM);
   if (k > kmax) k = kmax;
@@ -190,13 +190,14 @@ extern "C" int tnml_project(const void* B, const void* pp, const void* Lenv, con
   if (dtype == TNML_F32)
     return f32::project((const double*)B, (const float*)pp, (const float*)Lenv, (const float*)Renv, (float*)f, ws, Ns,
                         Dl, Dr, L, max_ctas, (cudaStream_t)stream);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (attr_once.needed(attr_dev)) {
     cudaError_t e = cudaFuncSetAttribute(k_project<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
     e = cudaFuncSetAttribute(k_project<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM_BYTES);
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
   int cols, ks;
   int64_t chunk;

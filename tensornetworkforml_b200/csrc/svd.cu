@@ -97,6 +97,10 @@ __device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no s
   return y;
 }
 
+}  // namespace tnml
+#include "svd_fast.cuh"
+namespace tnml {
+
 // Sum four values over the 32 lanes of a warp and leave all four sums on every lane: packed butterfly, 10 double
 // shuffles instead of 20 (shuffles share the MIO queue with shared-memory traffic, which bounds this kernel).
 __device__ __forceinline__ void warp_sum4(double& g0, double& g1, double& g2, double& g3, int lane) {
@@ -201,7 +205,9 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
                                                       const double* __restrict__ lam_prev, double* __restrict__ Wout,
                                                       int* __restrict__ flags_out, const int* __restrict__ sub,
                                                       int m_split, int* __restrict__ split_out,
-                                                      long long batch_stride = 0, int hold = 0) {
+                                                      long long batch_stride = 0, int hold = 0,
+                                                      const double* __restrict__ fastf = nullptr,
+                                                      double* __restrict__ warm_hdr = nullptr) {
   // hold > 1: launched as ONE cluster of `hold` CTAs of which only rank 0 works; the others wait at the cluster barrier
   // and thereby keep `hold` SMs of one GPC occupied until this kernel ends -- the cluster sweeps that follow on the same
   // stream then find a GPC with enough free SMs although the projection has filled the rest of the GPU meanwhile
@@ -215,6 +221,10 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     const size_t off = (size_t)blockIdx.x * (size_t)batch_stride;
     partial += off; Vt += off; lam += off; info += off; skip_flag += off;
     sub = reinterpret_cast<const int*>(reinterpret_cast<const double*>(sub) + off);
+  }
+  if (fastf && *fastf != 0.0) {                      // the warm-started fast split already delivered this pass
+    if (holder) cg::this_cluster().sync();
+    return;
   }
   if (sub) n = sub[0];                               // sub-block second pass
   // Second-pass protocol: the first pass sets *skip_flag = 1 when lambda_min / lambda_max > 1e-7 (sigma ratio
@@ -524,6 +534,7 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
     }
     if (lane == 0) *skip_flag = (mn > 1e-7 * mx) ? 1.0 : 0.0;
   }
+  if (warm_hdr && tid == 0) { warm_hdr[0] = 1.0; warm_hdr[1] = (double)n; warm_hdr[2] = (double)m_split; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1139,7 +1150,8 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
 __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict__ Wg, int NP, int n, int use_chol,
                                                        int pass_id, double* __restrict__ Vt, double* __restrict__ lam,
                                                        double* __restrict__ skip_flag, const double* __restrict__ lam_prev,
-                                                       double* __restrict__ info, int* __restrict__ sub, int m_defer) {
+                                                       double* __restrict__ info, int* __restrict__ sub, int m_defer,
+                                                       double* __restrict__ warm_hdr = nullptr, int m_keep = 0) {
   __shared__ double nrm[SVD_MAXN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
   if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) {
@@ -1205,6 +1217,8 @@ __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict_
       if (sub) { sub[0] = cnt; sub[1] = n - cnt; }
     }
   }
+  // the rotation of this pass now sits in the caller's warm buffer: mark it usable for the next visit of this bond
+  if (pass_id == 1 && warm_hdr && tid == 0) { warm_hdr[0] = 1.0; warm_hdr[1] = (double)n; warm_hdr[2] = (double)m_keep; }
 }
 
 // Wg (NP x NP, zero padded; NP == n gives the plain n x n matrix) = sum of the Gram partials in a fixed order;
@@ -1250,6 +1264,10 @@ constexpr int CHOL_BIG_CAP_256 = 100, CHOL_BIG_CAP_512 = 50;   // factor rows ca
 
 static cudaError_t jacobi_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_fast_split, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_fast_complement, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_chol_big<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_BIG_CAP_256 * 256 * 8);
   if (e != cudaSuccess) return e;
@@ -1400,13 +1418,14 @@ struct JacobiBuffers {
 static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, double* lam, double tol, int use_chol,
                          int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
                          cudaStream_t st, int m_defer = 0, int m_keep = 0, int* split_slot = nullptr,
-                         cudaEvent_t gram_done = nullptr) {
-  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+                         cudaEvent_t gram_done = nullptr, double* warm_hdr = nullptr, bool force_single = false,
+                         const double* fastf = nullptr) {
+  const bool cluster = !force_single && (n > 128 || (n > 64 && jacobi_cluster_enabled()));
   if (!cluster) {
     TNML_COUNT(1);
     if (n > 64)
       k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                   lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
+                                                   lam_prev, nullptr, nullptr, nullptr, 0, nullptr, 0LL, 0, fastf);
     else if (n > 32)
       k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
                                                 lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
@@ -1450,7 +1469,8 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
         const double* lam_prev_c = lam_prev;
         const int* sub_c = sub2;
         cudaError_t ce = cudaLaunchKernelEx(&cfg, k_jacobi<128>, scratch_c, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info,
-                                            skip, lam_prev_c, jb.Wg, jb.flags, sub_c, m_keep, split, 0LL, 8);
+                                            skip, lam_prev_c, jb.Wg, jb.flags, sub_c, m_keep, split, 0LL, 8,
+                                            (const double*)nullptr, (double*)nullptr);
         if (ce != cudaSuccess) return TNML_CUDA_ERR(ce);
       } else {
         if (gram_done) cudaEventRecord(gram_done, st);
@@ -1495,7 +1515,8 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
     else e = launch_cluster<16, 2>(16, 256, jb.Wg, jb.nrm2g, jb.flags, tol, info, skip, pass_id, sub2, st);
   }
   if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-  k_jacobi_finish<<<1, 512, 0, st>>>(jb.Wg, NP, n, use_chol, pass_id, Vt, lam, skip, lam_prev, info, sub, m_defer);
+  k_jacobi_finish<<<1, 512, 0, st>>>(jb.Wg, NP, n, use_chol, pass_id, Vt, lam, skip, lam_prev, info, sub, m_defer,
+                                     warm_hdr, m_keep);
   return tnml_launch_status();
 }
 
@@ -1607,7 +1628,8 @@ static SvdPlan svd_plan_rc(int R, int C) {
   p.off_lam1 = o; o += p.n;
   p.off_lam2 = o; o += p.n;
   p.off_Y = o; o += (size_t)p.n * p.Nl;
-  p.off_skip = o; o += 2;      // [0] second pass skipped on the critical path, [1] deferred tail pass skipped
+  p.off_skip = o; o += 4;      // [0] second pass skipped on the critical path, [1] deferred tail pass skipped,
+                               // [2] the warm-started fast split delivered the first pass (svd_fast.cuh)
   p.off_Wg = o; o += (size_t)p.NP * p.NP;
   p.off_nrm = o; o += p.NP;
   p.off_flags = o; o += 32;   // 64 ints
@@ -1620,19 +1642,33 @@ static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
   return svd_plan_rc(left_dir ? 2 * Dl * L : 2 * Dl, left_dir ? 2 * Dr : 2 * L * Dr);
 }
 
+static int fast_split_enabled() {   // TNML_FAST_SPLIT=0: never take the warm-started fast path (A/B knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_FAST_SPLIT");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+static bool fast_split_shape(int n, int m) { return n == FS_N && m == FS_M && fast_split_enabled(); }
+
 // Shared implementation: X = R x C row-major matrix, rowmap/colmap = where row i / column j of the factors land.
 static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_rows, Idx3 rowmap, long long row_k,
                     double* dst_cols, Idx3 colmap, long long col_k, double* svals, double* w, cudaStream_t st,
-                    cudaEvent_t gram_done = nullptr) {
+                    cudaEvent_t gram_done = nullptr, double* warm = nullptr, int fast_hint = 0) {
   if (p.n > SVD_MAXN) return TNML_ERR_UNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  const int attr_dev = tnml_current_device();
+  if (attr_once.needed(attr_dev)) {
     cudaError_t e = jacobi_prepare();
     if (e != cudaSuccess) return TNML_CUDA_ERR(e);
-    attr_set = true;
+    attr_once.mark(attr_dev);
   }
-  double *partial = w + p.off_partial, *vt1 = w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
+  // warm != nullptr: the first-pass rotation lives in the caller's per-bond buffer (n x n doubles + FS_HDR), where the
+  // next visit of the same bond finds it as its starting basis (svd_fast.cuh)
+  double *partial = w + p.off_partial, *vt1 = warm ? warm : w + p.off_vt1, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1,
          *lam2 = w + p.off_lam2, *Y = w + p.off_Y, *skip = w + p.off_skip;
+  double* warm_hdr = warm ? warm + (size_t)p.n * p.n : nullptr;
   JacobiBuffers jb{w + p.off_Wg, w + p.off_nrm, (int*)(w + p.off_flags), Y};
   const long long ss = p.rows_short ? p.C : 1, sl = p.rows_short ? 1 : p.C;
   const int n = p.n, Nl = p.Nl;
@@ -1643,7 +1679,10 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   const long long k_short_stride = p.rows_short ? row_k : col_k, k_long_stride = p.rows_short ? col_k : row_k;
   const int tiles = tnml_cdiv(n, GRAM_TILE);
   const dim3 ggrid(p.nparts, tiles, tiles);
-  const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
+  // fast mode: the warm-started deflation split first; the single-CTA pipeline behind it only runs when a gate failed
+  // (a cluster launch could not even be SCHEDULED to return early while the projection occupies the GPU)
+  const bool fast = fast_hint && warm && refine == 3 && fast_split_shape(n, m);
+  const bool cluster = !fast && (n > 128 || (n > 64 && jacobi_cluster_enabled()));
   const int m_defer = (refine == 3 && cluster) ? m : 0;     // refine 3 = refine 1 + deferred tail (svd_tail)
   if (refine == 3) refine = 1;
   double* skip1 = refine == 1 ? skip : nullptr;
@@ -1653,8 +1692,24 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
 
   TNML_COUNT(1);
   k_gram<<<ggrid, 256, 0, st>>>(X, ss, sl, n, Nl, p.lc, partial, nullptr, nullptr);
-  rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer, m,
-                     (int*)(w + p.off_sub) + 2, gram_done);
+  if (fast) {
+    TNML_COUNT(3);
+    double* Gs = Y;                                   // the Y buffer is free until a second pass runs
+    k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, p.nparts, n, n, Gs, jb.flags, nullptr, 1, nullptr, 1);
+    if (gram_done) cudaEventRecord(gram_done, st);
+    k_fast_split<<<1, FS_THREADS, FS_SMEM_BYTES, st>>>(Gs, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n);
+    k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(Gs, 1, n, vt1, lam1, 40, tol_final, 1, 1, svals + n, skip1, nullptr,
+                                                 nullptr, nullptr, nullptr, m, nullptr, 0LL, 0, skip + 2, warm_hdr);
+    rc = tnml_launch_status();
+  } else {
+    rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer,
+                       m, (int*)(w + p.off_sub) + 2, gram_done, warm_hdr);
+    if (rc == 0 && warm_hdr && !cluster) {            // single-CTA pipeline (n <= 64): the header is written separately
+      TNML_COUNT(1);
+      k_warm_header<<<1, 32, 0, st>>>(warm_hdr, n, m, nullptr);
+      rc = tnml_launch_status();
+    }
+  }
   // (paths that do not launch the holding Cholesky never record the event: the caller created it in the recorded state)
   if (rc) return rc;
   if (refine) {
@@ -1667,7 +1722,7 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
                                                                     only_if_pass2);
     k_gram<<<ggrid, 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip1, sub);
     rc = launch_jacobi(partial, p.nparts, n, vt2, lam2, tol_final, sub ? 1 : 0, 2, svals + n + 1, skip1, lam1, jb, sub,
-                       st);
+                       st, 0, 0, nullptr, nullptr, nullptr, fast, fast ? skip + 2 : nullptr);
     if (rc) return rc;
     k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(m, 32)), 256, 0, st>>>(Y, Nl, 1, n, Nl, vt2, lam2, m, dst_long,
                                                                     k_long_stride, map_long, first_pass_if_skipped);
@@ -1696,7 +1751,8 @@ __global__ void __launch_bounds__(256) k_tail_svals(const double* __restrict__ l
   for (int k = k0 + threadIdx.x; k < n; k += 256) svals[k] = sqrt(lam2[compact ? k - k0 : k]);
 }
 
-static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w, cudaStream_t st) {
+static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w, cudaStream_t st,
+                    double* warm = nullptr) {
   const int n = p.n, Nl = p.Nl;
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
   if (!cluster) return TNML_OK;                       // refine 3 never defers on the single-CTA path
@@ -1710,8 +1766,8 @@ static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w,
   const Idx3 dense{1, 1, 1, 0, 0};
   const RowsAlt if_deferred{skip2, 0, nullptr, 0, 0, nullptr, nullptr};
   TNML_COUNT(3);
-  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, w + p.off_vt1, nullptr, n, Y, Nl,
-                                                                  dense, if_deferred);
+  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, warm ? warm : w + p.off_vt1, nullptr,
+                                                                  n, Y, Nl, dense, if_deferred);
   k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
   // (Measured and rejected: solving the deferred block with the single-CTA kernel k_jacobi<64> instead of a second
   // cluster -- the split on the critical path went from 0.91 to 1.39 ms; TNML_TAIL_SINGLE_CTA=1 re-enables it.)
@@ -1770,7 +1826,8 @@ __global__ void __launch_bounds__(64) k_tail_batch_svals(const double* __restric
   if (threadIdx.x == 0) sv[n + 1] = rec[2];
 }
 
-static int svd_tail_record(const double* X, SvdPlan p, int m, double* rec, double* w, cudaStream_t st) {
+static int svd_tail_record(const double* X, SvdPlan p, int m, double* rec, double* w, cudaStream_t st,
+                           double* warm = nullptr, bool fast = false) {
   const int n = p.n, Nl = p.Nl;
   double *partial = w + p.off_partial, *Y = w + p.off_Y, *skip2 = w + p.off_skip + 1;
   int* sub = (int*)(w + p.off_sub);
@@ -1779,9 +1836,13 @@ static int svd_tail_record(const double* X, SvdPlan p, int m, double* rec, doubl
   const RowsAlt if_deferred{skip2, 0, nullptr, 0, 0, nullptr, nullptr};
   const int tiles = tnml_cdiv(n, GRAM_TILE);
   (void)m;
+  if (fast) {   // after a fast split the complement basis (rows m .. n-1 of the warm buffer) is refreshed first
+    TNML_COUNT(1);
+    k_fast_complement<<<1, FS_THREADS, FS_SMEM_BYTES, st>>>(warm, w + p.off_skip);
+  }
   TNML_COUNT(4);
-  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, w + p.off_vt1, nullptr, n, Y, Nl,
-                                                                  dense, if_deferred);
+  k_rows<<<dim3(tnml_cdiv(Nl, 32), tnml_cdiv(n, 32)), 256, 0, st>>>(X, ss, sl, n, Nl, warm ? warm : w + p.off_vt1, nullptr,
+                                                                  n, Y, Nl, dense, if_deferred);
   k_gram<<<dim3(p.nparts, tiles, tiles), 256, 0, st>>>(Y, Nl, 1, n, Nl, p.lc, partial, skip2, sub);
   k_sum_partials<<<tnml_cdiv(64 * 64, 256), 256, 0, st>>>(partial, p.nparts, n, n, rec + TAIL_REC_GRAM,
                                                           (int*)(w + p.off_flags), skip2, 3, sub, 1);
@@ -1806,9 +1867,14 @@ extern "C" int tnml_svd_split(const void* Bnew, void* site_p, void* site_q, void
   return tnml_svd_split_ev(Bnew, site_p, site_q, svals, ws, Dl, Dr, L, m, left_dir, refine, dtype, stream, nullptr);
 }
 
-extern "C" int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl,
-                                 int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype,
-                                 tnml_stream_t stream, void* gram_done_event) {
+extern "C" int64_t tnml_svd_warm_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir) {
+  const SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
+  return ((int64_t)p.n * p.n + FS_HDR) * 8;
+}
+
+extern "C" int tnml_svd_split_warm(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, void* warm,
+                                   int32_t Dl, int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine,
+                                   int32_t fast, int32_t dtype, tnml_stream_t stream, void* gram_done_event) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(Bnew && site_p && site_q && svals && ws && Dl > 0 && Dr > 0 && L > 0);
   SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
@@ -1824,7 +1890,14 @@ extern "C" int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, v
     colmap = Idx3{1, 1, 1, 0, 0}; col_k = 2LL * Dr;                                       // site_q[k][t][c]
   }
   return svd_core((const double*)Bnew, p, m, refine, (double*)site_p, rowmap, row_k, (double*)site_q, colmap, col_k,
-                  (double*)svals, (double*)ws, (cudaStream_t)stream, (cudaEvent_t)gram_done_event);
+                  (double*)svals, (double*)ws, (cudaStream_t)stream, (cudaEvent_t)gram_done_event, (double*)warm, fast);
+}
+
+extern "C" int tnml_svd_split_ev(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, int32_t Dl,
+                                 int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t refine, int32_t dtype,
+                                 tnml_stream_t stream, void* gram_done_event) {
+  return tnml_svd_split_warm(Bnew, site_p, site_q, svals, ws, nullptr, Dl, Dr, L, m, left_dir, refine, 0, dtype, stream,
+                             gram_done_event);
 }
 
 extern "C" int64_t tnml_svd_workspace_bytes(int32_t R, int32_t C) { return (int64_t)svd_plan_rc(R, C).total * 8; }
@@ -1841,18 +1914,26 @@ extern "C" int tnml_svd(const void* Mx, void* US, void* SVh, void* svals, void* 
                   (double*)ws, (cudaStream_t)stream);
 }
 
-extern "C" int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, int32_t Dl, int32_t Dr,
-                                   int32_t L, int32_t m, int32_t left_dir, int32_t dtype, tnml_stream_t stream) {
+extern "C" int tnml_svd_split_tail_warm(const void* Bnew, void* svals, void* ws, void* record, void* warm, int32_t Dl,
+                                        int32_t Dr, int32_t L, int32_t m, int32_t left_dir, int32_t fast, int32_t dtype,
+                                        tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
   TNML_REQUIRE(Bnew && svals && ws && Dl > 0 && Dr > 0 && L > 0 && m > 0);
   const SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
-  const bool cluster = p.n > 128 || (p.n > 64 && jacobi_cluster_enabled());
+  const bool fastm = fast && warm && record && fast_split_shape(p.n, m);
+  const bool cluster = fastm || p.n > 128 || (p.n > 64 && jacobi_cluster_enabled());
   if (record && cluster && p.n <= 128 && p.n - m <= 64)      // the deferred block has at most n - m <= 64 rows
-    return svd_tail_record((const double*)Bnew, p, m, (double*)record, (double*)ws, (cudaStream_t)stream);
+    return svd_tail_record((const double*)Bnew, p, m, (double*)record, (double*)ws, (cudaStream_t)stream, (double*)warm,
+                           fastm);
   if (record) {                                              // nothing recorded: mark the record as empty
     k_tail_record_hdr_empty<<<1, 32, 0, (cudaStream_t)stream>>>((double*)record);
   }
-  return svd_tail((const double*)Bnew, p, m, (double*)svals, (double*)ws, (cudaStream_t)stream);
+  return svd_tail((const double*)Bnew, p, m, (double*)svals, (double*)ws, (cudaStream_t)stream, (double*)warm);
+}
+
+extern "C" int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, int32_t Dl, int32_t Dr,
+                                   int32_t L, int32_t m, int32_t left_dir, int32_t dtype, tnml_stream_t stream) {
+  return tnml_svd_split_tail_warm(Bnew, svals, ws, record, nullptr, Dl, Dr, L, m, left_dir, 0, dtype, stream);
 }
 
 /* Batched deferred tail: tnml_svd_split_tail with a record pointer only stores the small block's Gram matrix; this call

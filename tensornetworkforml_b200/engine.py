@@ -137,6 +137,11 @@ class SweepEngine:
         self._tail = None
         self.n_svd_ws = 4             # SVD workspaces in rotation: a tail refinement may lag this many splits - 1
         self._tail_evt = [None] * self.n_svd_ws
+        # warm-started split (tnml_svd_split_warm): per (bond, direction) the short-side rotation of the previous visit;
+        # the second and later visits of a bond try the deflation path first (svd_fast.cuh), verified on the device
+        self.warm_split = os.environ.get("TNML_FAST_SPLIT", "1") != "0"
+        self._warm = {}
+        self.project_ctas_fast = int(os.environ.get("TNML_PROJECT_CTAS_FAST", "146"))   # one CTA of the fast split + spare
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -213,6 +218,7 @@ class SweepEngine:
         assert len(host_sites) == self.S
         self.l_pos = int(l_pos)
         self.label_layout = "R"
+        self._warm = {}               # new weights: the rotations of earlier visits say nothing about them
         for p, A in enumerate(host_sites):
             A = np.ascontiguousarray(A, dtype=np.float64)
             if p == self.l_pos:
@@ -531,9 +537,21 @@ class SweepEngine:
                 self._gram_evt = torch.cuda.Event()
                 self._gram_evt.record(side)              # creates the CUDA event (in the recorded state)
             gram_done = self._gram_evt
+        # warm buffer of this (bond, direction); `fast` = the bond was split before in this direction with these shapes
+        warm, fast = None, 0
+        if defer and self.warm_split and min(R, Cc) == 128 and m == 64:
+            key = (p, ldir, Dl, Dr)
+            warm = self._warm.get(key)
+            if warm is None:
+                nw = self._ws_bytes("tnml_svd_warm_bytes", Dl, Dr, L, ldir) // 8
+                warm = self._warm[key] = torch.zeros(nw, dtype=torch.float64, device=self.device)
+                if side is not main:
+                    side.wait_stream(main)              # the zero fill ran on the main stream
+            else:
+                fast = 1
         with _Timed(self, "svd_split", 0.0, side):
-            call("tnml_svd_split_ev", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), Dl, Dr, L, m, ldir,
-                 3 if defer else self.svd_refine, F64, side.cuda_stream,
+            call("tnml_svd_split_warm", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), _ptr(warm), Dl, Dr, L,
+                 m, ldir, 3 if defer else self.svd_refine, fast, F64, side.cuda_stream,
                  gram_done.cuda_event if gram_done is not None else None)
         if defer:
             split_done = self._split_evt[par]
@@ -545,10 +563,14 @@ class SweepEngine:
             # becomes eligible a few microseconds after the event (without the pause the order was a race that the
             # first process on a fresh box lost: 454 instead of 345 ms per sweep)
             main.wait_event(gram_done)
-            call("tnml_delay", self.project_delay_ns, st)
+            if not fast:
+                call("tnml_delay", self.project_delay_ns, st)
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
-            # beside a cluster-parallel SVD the projection leaves the 8 SMs of the split's cluster free
+            # beside a cluster-parallel SVD the projection leaves the 8 SMs of the split's cluster free; beside the
+            # single-CTA fast split two SMs
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
+            if fast and cap:
+                cap = self.project_ctas_fast
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
                  Dl, Dr, L, cap, self.DT, st)
         if defer:
@@ -562,8 +584,10 @@ class SweepEngine:
             self.hist["tail_recs"].record_stream(tail)
             # only the small block's Gram matrix is recorded here; history() solves all records of the sweep at once
             rec_ptr = self.hist["tail_recs"].data_ptr() + step * self.hist["tail_recs"].shape[1] * 8
-            call("tnml_svd_split_tail", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, Dl, Dr, L, m, ldir, F64,
-                 tail.cuda_stream)
+            if warm is not None:
+                warm.record_stream(tail)
+            call("tnml_svd_split_tail_warm", _ptr(Bn), sv_ptr, _ptr(ws_svd), rec_ptr, _ptr(warm), Dl, Dr, L, m, ldir,
+                 fast, F64, tail.cuda_stream)
             evt = self._tail_evt[par]
             if evt is None:
                 evt = torch.cuda.Event()

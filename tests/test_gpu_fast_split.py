@@ -1,0 +1,144 @@
+"""GPU: the warm-started split (tnml_svd_split_warm / tnml_svd_split_tail_warm, csrc/svd_fast.cuh) against
+np.linalg.svd -- the replacement of NC:887-925 / NC:947-960 for a bond that is split again and again.
+
+Tolerances: singular values 2e-13 * sigma_max, kept product 1e-11 relative (the same bars as test_svd_split)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tensornetworkforml_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bond_like(rng, Dl, Dr, nl, left_dir, spread=0.5, tail=1e-6):
+    """A matrix with the spectrum of a trained bond tensor: n/2 singular values in [spread, 1], the rest ~tail."""
+    R, C = (2 * Dl, 2 * nl * Dr) if not left_dir else (2 * Dl * nl, 2 * Dr)
+    n = min(R, C)
+    Q1, _ = np.linalg.qr(rng.standard_normal((R, n)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((C, n)))
+    S = np.concatenate([np.linspace(1.0, spread, n // 2), tail * np.logspace(0, -2, n - n // 2)])
+    return (Q1 * S) @ Q2.T
+
+
+class Splitter:
+    """One (bond, direction): workspace, warm buffer and the split / tail / batch call sequence of engine.split_phase."""
+
+    def __init__(self, L, Dl, Dr, nl, left_dir, m):
+        self.L, self.Dl, self.Dr, self.nl, self.left_dir, self.m = L, Dl, Dr, nl, left_dir, m
+        lib = L.lib()
+        self.ws = torch.empty(lib.tnml_svd_split_workspace_bytes(Dl, Dr, nl, left_dir) // 8 + 1, dtype=torch.float64,
+                              device="cuda")
+        self.warm = torch.zeros(lib.tnml_svd_warm_bytes(Dl, Dr, nl, left_dir) // 8, dtype=torch.float64, device="cuda")
+        self.n = min(2 * Dl * (nl if left_dir else 1), 2 * Dr * (1 if left_dir else nl))
+
+    def run(self, Mx, fast):
+        L, Dl, Dr, nl, left_dir, m, n = self.L, self.Dl, self.Dr, self.nl, self.left_dir, self.m, self.n
+        Bd = torch.from_numpy(np.ascontiguousarray(Mx)).to("cuda")
+        site_p = torch.empty(Dl * 2 * m * (nl if left_dir else 1), dtype=torch.float64, device="cuda")
+        site_q = torch.empty(m * 2 * Dr * (1 if left_dir else nl), dtype=torch.float64, device="cuda")
+        sv = torch.full((4 * max(Dl, Dr, nl) * 2,), float("nan"), dtype=torch.float64, device="cuda")
+        rec = torch.zeros(L.lib().tnml_svd_tail_record_bytes() // 8, dtype=torch.float64, device="cuda")
+        L.call("tnml_svd_split_warm", Bd.data_ptr(), site_p.data_ptr(), site_q.data_ptr(), sv.data_ptr(),
+               self.ws.data_ptr(), self.warm.data_ptr(), Dl, Dr, nl, m, left_dir, 3, fast, L.F64, st(), None)
+        torch.cuda.synchronize()
+        marker = float(sv[n].item())                    # 100 + sweeps when the fast path delivered the split
+        L.call("tnml_svd_split_tail_warm", Bd.data_ptr(), sv.data_ptr(), self.ws.data_ptr(), rec.data_ptr(),
+               self.warm.data_ptr(), Dl, Dr, nl, m, left_dir, fast, L.F64, st())
+        L.call("tnml_svd_tail_batch", rec.data_ptr(), 1, sv.data_ptr(), sv.numel(), L.F64, st())
+        torch.cuda.synchronize()
+        sp, sq = site_p.cpu().numpy(), site_q.cpu().numpy()
+        if not left_dir:
+            US = sp.reshape(2 * Dl, m)                                                    # [(a,s)][k]
+            SVh = sq.reshape(m, 2, nl, Dr).transpose(0, 2, 1, 3).reshape(m, -1)           # [k][(l,t,c)] as in Mx
+            # Mx columns are (l, t, c) in the B[a,s,l,t,c] layout
+            prod = US @ SVh
+        else:
+            US = sp.reshape(Dl, nl, 2, m).transpose(0, 2, 1, 3).reshape(-1, m)            # [(a,s,l)][k]
+            SVh = sq.reshape(m, 2 * Dr)
+            prod = US @ SVh
+        return sv.cpu().numpy()[:n], prod, marker, US
+
+
+def check(Mx, sv, prod, m, US):
+    U, S, Vh = np.linalg.svd(Mx, full_matrices=False)
+    assert np.abs(sv - S).max() / S.max() < 2e-13
+    want = (U[:, :m] * S[:m]) @ Vh[:m]
+    assert np.abs(prod - want).max() / np.abs(want).max() < 1e-11
+    G = US.T @ US                                                    # sqrt(S) on both factors (NC:912-915)
+    assert np.abs(G - np.diag(S[:m])).max() / S.max() < 1e-10
+
+
+@pytest.mark.parametrize("left_dir", [0, 1])
+@pytest.mark.parametrize("spread", [0.5, 0.997])
+def test_fast_path_is_taken_and_matches_svd(L, left_dir, spread):
+    """Visit 1 (cold) fills the warm buffer; visits 2.. of a slowly drifting matrix take the deflation path (marker) and
+    agree with np.linalg.svd, including the discarded tail after the deferred refinement.  spread = 0.997 is the
+    interior of the bench chain: all kept singular values within 0.3 % of each other."""
+    rng = np.random.default_rng(20 + left_dir)
+    Dl = Dr = 64
+    nl, m = 10, 64
+    sp = Splitter(L, Dl, Dr, nl, left_dir, m)
+    Mx = bond_like(rng, Dl, Dr, nl, left_dir, spread)
+    sv, prod, marker, US = sp.run(Mx, fast=0)
+    assert marker < 100
+    check(Mx, sv, prod, m, US)
+    for visit in range(3):
+        # drift: a rank-n/2 change of relative size 1e-3 (rotates the dominant subspace) plus full-rank noise at 1e-6
+        Mx = Mx + 1e-3 * bond_like(rng, Dl, Dr, nl, left_dir, spread) + 1e-6 * np.abs(Mx).max() * rng.standard_normal(Mx.shape)
+        sv, prod, marker, US = sp.run(Mx, fast=1)
+        assert marker >= 100, "visit %d fell back to the cold pipeline" % visit
+        check(Mx, sv, prod, m, US)
+
+
+@pytest.mark.parametrize("left_dir", [0, 1])
+def test_gates_fall_back_to_the_cold_pipeline(L, left_dir):
+    """fast = 1 on inputs the deflation path must refuse: an unvisited warm buffer, no gap at m, a stale basis of an
+    unrelated matrix (accepted only if the device-side gates pass; the result must be right either way)."""
+    rng = np.random.default_rng(30 + left_dir)
+    Dl = Dr = 64
+    nl, m = 10, 64
+    sp = Splitter(L, Dl, Dr, nl, left_dir, m)
+    Mx = bond_like(rng, Dl, Dr, nl, left_dir)
+    sv, prod, marker, US = sp.run(Mx, fast=1)             # header invalid: nothing to start from
+    assert marker < 100
+    check(Mx, sv, prod, m, US)
+    R, C = Mx.shape
+    Mg = rng.standard_normal((R, C))                      # no gap anywhere
+    sv, prod, marker, US = sp.run(Mg, fast=1)
+    assert marker < 100
+    check(Mg, sv, prod, m, US)
+    Mx2 = bond_like(rng, Dl, Dr, nl, left_dir)            # unrelated subspace, big gap: may converge in two steps
+    sv, prod, marker, US = sp.run(Mx2, fast=1)
+    check(Mx2, sv, prod, m, US)
+    Ms = bond_like(rng, Dl, Dr, nl, left_dir, spread=1e-4)   # kept values down to 1e-4 sigma_max: outside the fast regime
+    sv, prod, marker, US = sp.run(Ms, fast=1)
+    assert marker < 100
+    check(Ms, sv, prod, m, US)
+
+
+def test_fast_split_is_deterministic(L):
+    rng = np.random.default_rng(40)
+    Dl = Dr = 64
+    nl, m = 10, 64
+    Mx = bond_like(rng, Dl, Dr, nl, 0)
+    Mx2 = Mx + 1e-5 * rng.standard_normal(Mx.shape)
+    outs = []
+    for _ in range(2):
+        sp = Splitter(L, Dl, Dr, nl, 0, m)
+        sp.run(Mx, fast=0)
+        sv, prod, marker, US = sp.run(Mx2, fast=1)
+        assert marker >= 100
+        outs.append((sv.copy(), prod.copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
