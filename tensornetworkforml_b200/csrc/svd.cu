@@ -97,10 +97,6 @@ __device__ __forceinline__ float rsqrt_approx(float x) {   // one MUFU.RSQ, no s
   return y;
 }
 
-}  // namespace tnml
-#include "svd_fast.cuh"
-namespace tnml {
-
 // Sum four values over the 32 lanes of a warp and leave all four sums on every lane: packed butterfly, 10 double
 // shuffles instead of 20 (shuffles share the MIO queue with shared-memory traffic, which bounds this kernel).
 __device__ __forceinline__ void warp_sum4(double& g0, double& g1, double& g2, double& g3, int lane) {
@@ -191,6 +187,10 @@ __device__ __forceinline__ bool rotateN(double (&x)[NR][E], double (&y)[NR][E], 
   }
   return any;
 }
+
+}  // namespace tnml
+#include "svd_fast.cuh"
+namespace tnml {
 
 // NP: padded matrix size (32, 64, 128).  Rows are grouped in NP/4 blocks of 4; one WARP owns one block pair per
 // block-round (circle method over the blocks), keeps the 8 rows in registers (lane holds elements lane + 32k) and

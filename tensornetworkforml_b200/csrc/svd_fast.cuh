@@ -23,7 +23,8 @@ namespace tnml {
 constexpr int FS_N = 128, FS_M = 64;
 constexpr int FS_LDV = FS_N + 4;   // row stride of the 64 x 128 panels (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int FS_LDS = FS_M + 4;   // row stride of the 64 x 64 matrices
-constexpr int FS_THREADS = 512;
+constexpr int FS_THREADS = 256;   // 8 warps: up to 255 registers per thread (the Jacobi blocks and the Y panel live there)
+constexpr int FS_WARPS = FS_THREADS / 32;
 constexpr int FS_OFF_A1 = 0;
 constexpr int FS_OFF_A2 = FS_OFF_A1 + FS_M * FS_LDV;
 constexpr int FS_OFF_S = FS_OFF_A2 + FS_M * FS_LDV;
@@ -31,8 +32,9 @@ constexpr int FS_OFF_W = FS_OFF_S + FS_M * FS_LDS;
 constexpr int FS_OFF_MISC = FS_OFF_W + FS_M * FS_LDS;
 constexpr int FS_MISC = 768;
 constexpr int FS_SMEM_BYTES = (FS_OFF_MISC + FS_MISC) * 8;
-// misc region (doubles): [0,64) dinv | [64,128) lcol | [128,320) diagP[2][96] | [320,352) red | [352,416) lam |
-//                        [416,480) ord (ints) | [480,..) scalars
+// misc region (doubles): [0,64) pivots | [64,128) row norms | [128,384) pivot row of Y, double-buffered | [384,416) red |
+//                        [416,480) lam | [480,544) 1/norm | [544,576) ord (ints) | [576,580) scalars |
+//                        [592,720) pivot column of S, double-buffered
 constexpr int FS_HDR = 8;          // doubles behind the n x n warm matrix: {valid, n, m, ...}
 
 __device__ __forceinline__ double fs_rsqrt(double x) {   // x > 0, normal: MUFU seed + one third-order correction
@@ -50,7 +52,8 @@ __device__ __forceinline__ double fs_rsqrt(double x) {   // x > 0, normal: MUFU 
 // Out[i][j] = sum_k V[i][k] G[k][j], i < 64, j, k < 128; V, Out in shared memory (stride FS_LDV), G symmetric in
 // global memory (L2): warp w owns the 8 output columns 8w .. 8w+7, i.e. 8 rows of G, read exactly once.
 __device__ __forceinline__ void fs_gemm_vg(const double* __restrict__ V, const double* __restrict__ G,
-                                           double* __restrict__ Out, int warp, int lane) {
+                                           double* __restrict__ Out, int warp_, int lane) {
+ for (int warp = warp_; warp < 16; warp += FS_WARPS) {
   const int r = lane >> 2, c = lane & 3;
   const double* g = G + (size_t)(warp * 8 + r) * FS_N + c;
   double acc[8][2];
@@ -78,11 +81,13 @@ __device__ __forceinline__ void fs_gemm_vg(const double* __restrict__ V, const d
     o[0] = acc[t][0];
     o[1] = acc[t][1];
   }
+ }
 }
 
 // C[i][j] = sum_{k < 128} A[i][k] B[j][k], i, j < 64 (A, B: stride FS_LDV; C: stride FS_LDS).  16 warps x 4 tiles.
 __device__ __forceinline__ void fs_gemm_abt(const double* __restrict__ A, const double* __restrict__ B,
-                                            double* __restrict__ C, int warp, int lane) {
+                                            double* __restrict__ C, int warp_, int lane) {
+ for (int warp = warp_; warp < 16; warp += FS_WARPS) {
   const int r = lane >> 2, c = lane & 3;
   const int ib = warp >> 1, jh = warp & 1;
   double acc[4][2];
@@ -102,13 +107,15 @@ __device__ __forceinline__ void fs_gemm_abt(const double* __restrict__ A, const 
     o[0] = acc[t][0];
     o[1] = acc[t][1];
   }
+ }
 }
 
 // acc(i, j) = sum_{k < 64} A[rowmap(i)][k] B[k][j], i < 64, j < 128 (A: stride FS_LDS, B: stride FS_LDV); the
 // epilogue receives (i, j, value) for the two values of each lane.  16 warps: 8 row tiles x 2 column halves.
 template <class Epi>
 __device__ __forceinline__ void fs_gemm_ab(const double* __restrict__ A, const int* __restrict__ rowmap,
-                                           const double* __restrict__ B, int warp, int lane, Epi epi) {
+                                           const double* __restrict__ B, int warp_, int lane, Epi epi) {
+ for (int warp = warp_; warp < 16; warp += FS_WARPS) {
   const int r = lane >> 2, c = lane & 3;
   const int ib = warp >> 1, jh = warp & 1;
   double acc[8][2];
@@ -129,157 +136,250 @@ __device__ __forceinline__ void fs_gemm_ab(const double* __restrict__ A, const i
     epi(i, j, acc[t][0]);
     epi(i, j + 1, acc[t][1]);
   }
+ }
 }
 
-// In-place right-looking Cholesky of the 64 x 64 matrix S (stride FS_LDS): lower triangle <- L, dinv[k] = 1 / L[k][k].
-// Returns false (uniformly) when a pivot drops below 1e-10 of the largest diagonal entry (the panel was far from
-// orthogonal: CholeskyQR would not deliver an orthonormal basis).
-__device__ __forceinline__ bool fs_cholesky(double* __restrict__ S, double* __restrict__ dinv, double* __restrict__ lcol,
-                                            int tid) {
+__device__ __forceinline__ double fs_rcp(double x) {   // x > 0, normal: MUFU seed + two Newton steps
+  const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
+  const double xs = x * __hiloint2double((1023 - ex) << 20, 0);      // in [1, 2)
+  float r0;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"((float)xs));
+  double r = (double)r0;
+  r = r * fma(-xs, r, 2.0);
+  r = r * fma(-xs, r, 2.0);
+  return r * __hiloint2double((1023 - ex) << 20, 0);
+}
+
+// CholeskyQR without the square roots on the critical path: S = Y Y^T = L D L^T (unit lower L) is eliminated and the
+// SAME elimination steps are applied to the rows of Y.  Both live in REGISTERS: thread = (column pair c, c + 64; rows
+// 4 j + g) of Y and (row si, columns sq + 4 u <= si) of the lower triangle of S; per step only the pivot column of S and
+// the pivot row of Y travel through (double-buffered) shared memory, so a step is ONE barrier and the chain
+// load pivot -> reciprocal -> multiplier -> FMA -> publish.  Out = D^-1/2 L^-1 Y has orthonormal rows.
+// Returns false (uniformly) when a pivot falls below 1e-10 of the largest diagonal entry (Y was far from orthogonal: no
+// orthonormal basis to working accuracy).
+__device__ __forceinline__ bool fs_orthonormalize(const double* __restrict__ S, const double* __restrict__ Yin,
+                                                  double* __restrict__ Out, double* __restrict__ yrow,
+                                                  double* __restrict__ col, double* __restrict__ dsave, int tid) {
+  const int c = tid & 63, g = tid >> 6;                                   // Y: columns c, c + 64; rows 4 j + g
+  const int si = tid >> 2, sq = tid & 3;                                  // S: row si, columns sq + 4 u
+  double y[16][2], sreg[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { y[j][0] = Yin[(4 * j + g) * FS_LDV + c]; y[j][1] = Yin[(4 * j + g) * FS_LDV + c + 64]; }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) sreg[u] = (sq + 4 * u <= si) ? S[si * FS_LDS + sq + 4 * u] : 0.0;
   double dmax = 0.0;
   for (int k = 0; k < FS_M; ++k) dmax = fmax(dmax, S[k * FS_LDS + k]);   // broadcast reads
   const double floor_ = dmax * 1e-10;
+  if (g == 0) { yrow[c] = y[0][0]; yrow[c + 64] = y[0][1]; }
+  if (sq == 0) col[si] = sreg[0];                                         // column 0 of S
+  __syncthreads();
   for (int k = 0; k < FS_M; ++k) {
-    const double d = S[k * FS_LDS + k];
+    const double* ccur = col + (k & 1) * FS_M;
+    double* cnext = col + ((k + 1) & 1) * FS_M;
+    const double d = ccur[k];
     if (!(d > floor_)) return false;
-    const double inv = fs_rsqrt(d);
-    if (tid >= k && tid < FS_M) lcol[tid] = S[tid * FS_LDS + k] * inv;
-    if (tid == 0) dinv[k] = inv;
-    __syncthreads();
-    for (int e = tid; e < FS_M * FS_M; e += FS_THREADS) {
-      const int i = e >> 6, j = e & 63;
-      if (j > k && i >= j) S[i * FS_LDS + j] = fma(-lcol[i], lcol[j], S[i * FS_LDS + j]);
-      else if (j == k && i >= k) S[i * FS_LDS + k] = lcol[i];
+    const double r = fs_rcp(d);
+    if (tid == 0) dsave[k] = d;
+    const double yk0 = yrow[(k & 1) * FS_N + c], yk1 = yrow[(k & 1) * FS_N + c + 64];
+    double pub0 = 0.0, pub1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int i = 4 * j + g;
+      if (i > k) {
+        const double mi = ccur[i] * r;
+        y[j][0] = fma(-mi, yk0, y[j][0]);
+        y[j][1] = fma(-mi, yk1, y[j][1]);
+      }
+      if (i == k + 1) { pub0 = y[j][0]; pub1 = y[j][1]; }
+    }
+    if (g == ((k + 1) & 3) && k + 1 < FS_M) {
+      yrow[((k + 1) & 1) * FS_N + c] = pub0;
+      yrow[((k + 1) & 1) * FS_N + c + 64] = pub1;
+    }
+    if (si > k) {                                                         // S[i][j] -= S[i][k] S[j][k] / d, k < j <= i
+      const double mi = ccur[si] * r;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int j = sq + 4 * u;
+        if (j > k && j <= si) sreg[u] = fma(-mi, ccur[j], sreg[u]);
+        if (j == k + 1 && j <= si) cnext[si] = sreg[u];
+      }
     }
     __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const double sc = fs_rsqrt(dsave[4 * j + g]);
+    Out[(4 * j + g) * FS_LDV + c] = y[j][0] * sc;
+    Out[(4 * j + g) * FS_LDV + c + 64] = y[j][1] * sc;
   }
   return true;
 }
 
-// Out = L^-1 In (forward substitution, 64 x 128 panels, stride FS_LDV): 4 threads per column, each takes every fourth
-// term of the inner sum; the partial sums meet through two shuffles.
-__device__ __forceinline__ void fs_forward_subst(const double* __restrict__ Lm, const double* __restrict__ dinv,
-                                                 const double* __restrict__ In, double* __restrict__ Out, int tid) {
-  const int s = tid >> 2, t = tid & 3;
-  for (int i = 0; i < FS_M; ++i) {
-    double acc = 0.0, acc2 = 0.0;
-    int k = t;
-    for (; k + 4 < i; k += 8) {
-      acc = fma(Lm[i * FS_LDS + k], Out[k * FS_LDV + s], acc);
-      acc2 = fma(Lm[i * FS_LDS + k + 4], Out[(k + 4) * FS_LDV + s], acc2);
+// Four independent row-pair rotations held in registers, like rotateN<4, E>, but the scalar work of the four rotations
+// is spread over the lanes: the packed butterfly leaves the inner product of rotation j on the lanes 8j .. 8j+7, which
+// compute that rotation's parameters ONCE per warp instruction (rotateN computes each of the four on all 32 lanes, one
+// after the other: ~4 x 50 instructions, 4 x 8 of them on the quarter-rate conversion / MUFU pipe -- the single-CTA
+// sweeps are bound by instruction issue and that pipe, not by latency), then cos, sin and the norm update are handed to
+// all lanes with three shuffles per rotation.
+template <int E>
+__device__ __forceinline__ bool rotate4_lanes(double (&x)[4][E], double (&y)[4][E], double (&nx)[4], double (&ny)[4],
+                                              double tol2, int lane) {
+  double g[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      if (k & 1) a1 = fma(x[i][k], y[i][k], a1);
+      else a0 = fma(x[i][k], y[i][k], a0);
     }
-    if (k < i) acc = fma(Lm[i * FS_LDS + k], Out[k * FS_LDV + s], acc);
-    acc += acc2;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    const double q = (In[i * FS_LDV + s] - acc) * dinv[i];
-    if (t == 0) Out[i * FS_LDV + s] = q;
-    __syncwarp();
+    g[i] = a0 + a1;
   }
-}
-
-// Rotation that annihilates the (p, q) entry of a symmetric matrix: tan, cos, sin in single precision after a
-// power-of-two rescale, then one exact renormalisation in double (every rotation is orthogonal to double precision;
-// the angle carries a relative error ~1e-7, which the quadratic convergence of the following sweep absorbs).
-__device__ __forceinline__ void fs_rot(double tpp, double tqq, double tpq, double& c, double& s, bool& big) {
-  const int ex = (__double2hiint(fabs(tpp) + fabs(tqq)) >> 20) & 0x7ff;
-  const double g2 = tpq * tpq, ab = fabs(tpp * tqq);
-  const bool rot = (g2 > 1e-32 * ab) && ex > 0 && ex < 2040;
+  const bool hi = lane & 16;
+  double ka = hi ? g[2] : g[0], kb = hi ? g[3] : g[1];
+  ka += __shfl_xor_sync(0xffffffffu, hi ? g[0] : g[2], 16);
+  kb += __shfl_xor_sync(0xffffffffu, hi ? g[1] : g[3], 16);
+  const bool h8 = lane & 8;
+  double ga = h8 ? kb : ka;
+  ga += __shfl_xor_sync(0xffffffffu, h8 ? ka : kb, 8);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 4);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 2);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 1);                   // rotation (lane >> 3)'s inner product
+  const double al = hi ? (h8 ? nx[3] : nx[2]) : (h8 ? nx[1] : nx[0]);
+  const double be = hi ? (h8 ? ny[3] : ny[2]) : (h8 ? ny[1] : ny[0]);
+  const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
+  const double g2 = ga * ga, ab = al * be;
+  const bool rot = (g2 > tol2 * ab) && ex > 0 && ex < 2040;
   const double sc = __hiloint2double((2046 - ex) << 20, 0);
-  const float df = (float)((tqq - tpp) * sc), tf = (float)((tpq + tpq) * sc);
+  const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
   const float hh = fmaf(df, df, tf * tf);
   const float h = hh * rsqrt_approx(hh);
   const float t0 = __fdividef(tf, df + copysignf(h, df));
   const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
-  const double cc = (double)cf, ss = (double)(cf * t0);
-  const double e = fma(cc, cc, fma(ss, ss, -1.0));
+  const double c = (double)cf, sv = (double)(cf * t0);
+  const double e = fma(c, c, fma(sv, sv, -1.0));
   const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
-  c = rot ? cc * nu : 1.0;
-  s = rot ? ss * nu : 0.0;
-  big = rot && (g2 > 1e-16 * ab);
-}
-
-// Role of index x in rotation set rn of the round-robin ordering over 64 indices (63 sets; pair 0 = (63, rn), pair k =
-// ((rn + k) % 63, (rn - k) % 63)): pair number, whether x is the first member, and its partner.
-__device__ __forceinline__ void fs_role(int x, int rn, int& pair, bool& first, int& partner) {
-  if (x == 63) { pair = 0; first = true; partner = rn; return; }
-  int d = x - rn;
-  if (d < 0) d += 63;
-  if (d == 0) { pair = 0; first = false; partner = 63; }
-  else if (d <= 31) { pair = d; first = true; partner = rn - d; if (partner < 0) partner += 63; }
-  else { pair = 63 - d; first = false; partner = rn + pair; if (partner >= 63) partner -= 63; }
-}
-
-// Two-sided cyclic Jacobi on the symmetric 64 x 64 matrix T (shared memory, stride FS_LDS): T <- J^T T J, Wt <- J^T Wt.
-// 16 warps; warp w owns the row pairs w and w + 16, lane b the column pair b: every thread rotates two 2 x 2 blocks of
-// T and two 2 x 2 blocks of Wt per rotation set.  The three numbers that define the rotation of each pair of the NEXT
-// set are forwarded through a double-buffered table (dp), so a set needs ONE block barrier.  Returns the sweeps used.
-__device__ __forceinline__ int fs_jacobi64(double* __restrict__ T, double* __restrict__ Wt, double* __restrict__ dp,
-                                           int max_sweeps, int tid) {
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int e = tid; e < FS_M * FS_M; e += FS_THREADS) Wt[(e >> 6) * FS_LDS + (e & 63)] = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
-  if (tid < 32) {   // rotation table of set 0
-    const int p = tid == 0 ? 63 : tid, q = tid == 0 ? 0 : 63 - tid;
-    dp[3 * tid] = T[p * FS_LDS + p];
-    dp[3 * tid + 1] = T[q * FS_LDS + q];
-    dp[3 * tid + 2] = T[p * FS_LDS + q];
-  }
-  __syncthreads();
-  int sweeps = 0, step = 0;
-  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-    bool bigany = false;
-    for (int r = 0; r < 63; ++r, ++step) {
-      const double* dcur = dp + ((step & 1) ? 96 : 0);
-      double* dnext = dp + ((step & 1) ? 0 : 96);
-      const int rn = (r == 62) ? 0 : r + 1;
-      // my column pair and its rotation
-      int pb, qb;
-      if (lane == 0) { pb = 63; qb = r; }
-      else { pb = r + lane; if (pb >= 63) pb -= 63; qb = r - lane; if (qb < 0) qb += 63; }
-      double cb, sb;
-      bool big;
-      fs_rot(dcur[3 * lane], dcur[3 * lane + 1], dcur[3 * lane + 2], cb, sb, big);
-      bigany |= big;
+  const double cj = rot ? c * nu : 1.0;
+  const double sj = rot ? sv * nu : 0.0;
+  const double tj = rot ? (double)t0 * ga : 0.0;
+  const bool any = __any_sync(0xffffffffu, rot && (g2 > 1e-16 * ab));
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int a = warp + 16 * h;
-        int pa, qa;
-        if (a == 0) { pa = 63; qa = r; }
-        else { pa = r + a; if (pa >= 63) pa -= 63; qa = r - a; if (qa < 0) qa += 63; }
-        const double ca = __shfl_sync(0xffffffffu, cb, a), sa = __shfl_sync(0xffffffffu, sb, a);
-        double* t1 = T + pa * FS_LDS;
-        double* t2 = T + qa * FS_LDS;
-        const double t11 = t1[pb], t12 = t1[qb], t21 = t2[pb], t22 = t2[qb];
-        const double u11 = fma(ca, t11, -sa * t21), u12 = fma(ca, t12, -sa * t22);
-        const double u21 = fma(sa, t11, ca * t21), u22 = fma(sa, t12, ca * t22);
-        const double v11 = fma(cb, u11, -sb * u12), v12 = fma(sb, u11, cb * u12);
-        const double v21 = fma(cb, u21, -sb * u22), v22 = fma(sb, u21, cb * u22);
-        t1[pb] = v11; t1[qb] = v12; t2[pb] = v21; t2[qb] = v22;
-        // forward what the next set's rotations need (roles of my two row indices in set rn are warp-uniform)
-        int pr1, pr2, pt1, pt2;
-        bool f1, f2;
-        fs_role(pa, rn, pr1, f1, pt1);
-        fs_role(qa, rn, pr2, f2, pt2);
-        if (lane == a) {   // diagonal block: the two diagonal entries
-          dnext[3 * pr1 + (f1 ? 0 : 1)] = v11;
-          dnext[3 * pr2 + (f2 ? 0 : 1)] = v22;
+  for (int i = 0; i < 4; ++i) {
+    const double cs = __shfl_sync(0xffffffffu, cj, 8 * i), sn = __shfl_sync(0xffffffffu, sj, 8 * i);
+    const double tg = __shfl_sync(0xffffffffu, tj, 8 * i);
+    nx[i] -= tg;
+    ny[i] += tg;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const double a = x[i][k], b = y[i][k];
+      x[i][k] = fma(cs, a, -sn * b);
+      y[i][k] = fma(sn, a, cs * b);
+    }
+  }
+  return any;
+}
+
+// One-sided (Hestenes) Jacobi on the rows of the 64 x 64 matrix X (shared memory, row stride FS_LDS): the register-block
+// scheme of k_jacobi<64> (8 warps, each owns a pair of 4-row blocks per block-round and performs all 16 cross rotations
+// before the rows go back to shared memory).  Applied to the symmetric Rayleigh-Ritz matrix T the rows converge to
+// lambda_k w_k^T.  Every thread of the CTA must call it (block barriers); warps 8.. only take part in the barriers.
+__device__ __forceinline__ int fs_jacobi_rows(double* __restrict__ X, double* __restrict__ nrm2, int* __restrict__ rot_count,
+                                              int max_sweeps, double tol2, int tid) {
+  constexpr int NP = FS_M, LD = FS_LDS, NB = NP / 4, NW = NB / 2, E = NP / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool act = warp < NW;     // (every warp when FS_THREADS == 256)
+  int sweeps_done = 0;
+  int ra = (warp == 0) ? 0 : warp - 1, rb = NB - 2 - warp;
+  if (tid == 0) *rot_count = 0;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    if (act) {
+      for (int r = warp; r < NP; r += NW) {   // refresh the cached squared row norms
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < E; ++k) { const double v = X[r * LD + lane + 32 * k]; s = fma(v, v, s); }
+        s = warp_sum(s);
+        if (lane == 0) nrm2[r] = s;
+      }
+    }
+    __syncthreads();
+    bool rotated = false;
+    for (int round = 0; round < NB - 1; ++round) {
+      if (act) {
+        const int bi = (warp == 0) ? 0 : 1 + ra;
+        const int bj = 1 + rb;
+        double a[4][E], b[4][E], na[4], nb[4];
+        double* const wa = X + 4 * bi * LD + lane;
+        double* const wb = X + 4 * bj * LD + lane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            a[i][k] = wa[i * LD + 32 * k];
+            b[i][k] = wb[i * LD + 32 * k];
+          }
+          na[i] = nrm2[4 * bi + i];
+          nb[i] = nrm2[4 * bj + i];
         }
-        if (f1) { if (pt1 == pb) dnext[3 * pr1 + 2] = v11; else if (pt1 == qb) dnext[3 * pr1 + 2] = v12; }
-        if (f2) { if (pt2 == pb) dnext[3 * pr2 + 2] = v21; else if (pt2 == qb) dnext[3 * pr2 + 2] = v22; }
-        // eigenvector accumulator: rows pa, qa, columns 2 lane, 2 lane + 1
-        double2* w1 = reinterpret_cast<double2*>(Wt + pa * FS_LDS) + lane;
-        double2* w2 = reinterpret_cast<double2*>(Wt + qa * FS_LDS) + lane;
-        const double2 x = *w1, y = *w2;
-        *w1 = make_double2(fma(ca, x.x, -sa * y.x), fma(ca, x.y, -sa * y.y));
-        *w2 = make_double2(fma(sa, x.x, ca * y.x), fma(sa, x.y, ca * y.y));
+        if (round == 0) {   // pairs inside each block, once per sweep
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const int p0 = 0, q0 = s + 1;
+            const int p1 = (s == 0) ? 2 : 1, q1 = (s == 2) ? 2 : 3;
+            double x[4][E], y[4][E], nx[4], ny[4];
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+              x[0][k] = a[p0][k]; y[0][k] = a[q0][k]; x[1][k] = a[p1][k]; y[1][k] = a[q1][k];
+              x[2][k] = b[p0][k]; y[2][k] = b[q0][k]; x[3][k] = b[p1][k]; y[3][k] = b[q1][k];
+            }
+            nx[0] = na[p0]; ny[0] = na[q0]; nx[1] = na[p1]; ny[1] = na[q1];
+            nx[2] = nb[p0]; ny[2] = nb[q0]; nx[3] = nb[p1]; ny[3] = nb[q1];
+            rotated |= rotate4_lanes<E>(x, y, nx, ny, tol2, lane);
+#pragma unroll
+            for (int k = 0; k < E; ++k) {
+              a[p0][k] = x[0][k]; a[q0][k] = y[0][k]; a[p1][k] = x[1][k]; a[q1][k] = y[1][k];
+              b[p0][k] = x[2][k]; b[q0][k] = y[2][k]; b[p1][k] = x[3][k]; b[q1][k] = y[3][k];
+            }
+            na[p0] = nx[0]; na[q0] = ny[0]; na[p1] = nx[1]; na[q1] = ny[1];
+            nb[p0] = nx[2]; nb[q0] = ny[2]; nb[p1] = nx[3]; nb[q1] = ny[3];
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {   // the 16 pairs across the two blocks: set s pairs a[i] with b[(i+s)&3]
+          double y[4][E], ny[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) y[i][k] = b[(i + s) & 3][k];
+            ny[i] = nb[(i + s) & 3];
+          }
+          rotated |= rotate4_lanes<E>(a, y, na, ny, tol2, lane);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int k = 0; k < E; ++k) b[(i + s) & 3][k] = y[i][k];
+            nb[(i + s) & 3] = ny[i];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) {
+            wa[i * LD + 32 * k] = a[i][k];
+            wb[i * LD + 32 * k] = b[i][k];
+          }
+          if (lane == 0) { nrm2[4 * bi + i] = na[i]; nrm2[4 * bj + i] = nb[i]; }
+        }
+        ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+        rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
       }
       __syncthreads();
     }
-    sweeps = sweep + 1;
-    // a sweep whose largest relative off-diagonal entry was below 1e-8 leaves all of them below ~1e-15
-    if (!__syncthreads_or(bigany ? 1 : 0)) break;
+    sweeps_done = sweep + 1;
+    // a sweep in which every rotated pair had a relative inner product below 1e-8 leaves all of them below ~1e-15
+    if (!__syncthreads_or(rotated ? 1 : 0)) break;
   }
-  return sweeps;
+  return sweeps_done;
 }
 
 // One CTA of FS_THREADS threads.  G: n x n Gram matrix (global); vt: warm buffer (n x n rows = vectors, then FS_HDR
@@ -293,10 +393,23 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   double* Sm = fsm + FS_OFF_S;
   double* Wm = fsm + FS_OFF_W;
   double* misc = fsm + FS_OFF_MISC;
-  double *dinv = misc, *lcol = misc + 64, *dp = misc + 128, *red = misc + 320, *lamv = misc + 352;
-  int* ord = reinterpret_cast<int*>(misc + 416);
+  double *dsave = misc, *nrm2 = misc + 64, *yrow = misc + 128, *red = misc + 384, *lamv = misc + 416, *invn = misc + 480;
+  int* ord = reinterpret_cast<int*>(misc + 544);
+  int* rot_count = reinterpret_cast<int*>(misc + 577);
+  double* scol = misc + 592;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* hdr = vt + (size_t)FS_N * FS_N;
+  // phase clocks (diagnostics in the unused slots behind the singular values: info[4 + i] = cycles of phase i)
+  long long tprev = clock64();
+  int tphase = 0;
+  auto tick = [&]() {
+    if (tid == 0 && info) {
+      const long long now = clock64();
+      info[4 + tphase] = (double)(now - tprev);
+      tprev = now;
+    }
+    ++tphase;
+  };
   auto fail = [&]() {
     if (tid == 0) { skip[2] = 0.0; skip[1] = 1.0; }
   };
@@ -308,23 +421,30 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     double s = 0.0;
     for (int i = lane; i < FS_N; i += 32) s += __ldcg(G + (size_t)i * FS_N + i);
     s = warp_sum(s);
-    if (lane == 0) misc[480] = s;
+    if (lane == 0) misc[576] = s;
   }
   __syncthreads();
+  tick();                                              // 0: load
   double resid2 = 0.0, trT = 0.0, mind = 0.0;
   bool ok = false;
   for (int iter = 0; iter < 2; ++iter) {
+    tphase = 1;
     fs_gemm_vg(A1, G, A2, warp, lane);                 // Y = V G
     __syncthreads();
+    tick();                                            // 1
     fs_gemm_abt(A2, A2, Sm, warp, lane);               // S = Y Y^T
     __syncthreads();
-    if (!fs_cholesky(Sm, dinv, lcol, tid)) { fail(); return; }
-    fs_forward_subst(Sm, dinv, A2, A1, tid);           // Q = L^-1 Y
+    tick();                                            // 2
+    if (!fs_orthonormalize(Sm, A2, A1, yrow, scol, dsave, tid)) { fail(); return; }   // Q = D^-1/2 L^-1 Y
     __syncthreads();
+    tick();                                            // 3
+    tick();                                            // 4
     fs_gemm_vg(A1, G, A2, warp, lane);                 // Z = Q G
     __syncthreads();
+    tick();                                            // 5
     fs_gemm_abt(A1, A2, Sm, warp, lane);               // T = Q Z^T
     __syncthreads();
+    tick();                                            // 6
     for (int e = tid; e < FS_M * FS_M; e += FS_THREADS) {   // symmetrise
       const int i = e >> 6, j = e & 63;
       if (i < j) {
@@ -349,12 +469,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     for (int k = 0; k < FS_M; ++k) { const double d = Sm[k * FS_LDS + k]; trT += d; mind = fmin(mind, d); }
     ok = mind > 0.0 && resid2 <= 1e-24 * mind * mind;   // |R|_F <= 1e-12 min diag(T)
     __syncthreads();
+    tick();                                            // 7: residual
     if (ok) break;                                      // otherwise iterate once more from Q (A1)
   }
   if (!ok) { fail(); return; }
-  const int sweeps = fs_jacobi64(Sm, Wm, dp, 30, tid);
-  // eigenvalues = diagonal of T; rank them (descending, ties by index)
-  if (tid < FS_M) lamv[tid] = Sm[tid * FS_LDS + tid];
+  const int sweeps = fs_jacobi_rows(Sm, nrm2, rot_count, 30, 64.0 * 4.930380657631324e-32, tid);
+  tphase = 8;
+  tick();                                              // 8: Jacobi
+  // rows of Sm are now lambda_k w_k^T: eigenvalue = row norm; rank them (descending, ties by index)
+  for (int r = warp; r < FS_M; r += FS_THREADS / 32) {
+    const double v0 = Sm[r * FS_LDS + lane], v1 = Sm[r * FS_LDS + lane + 32];
+    const double s = warp_sum(fma(v0, v0, v1 * v1));
+    if (lane == 0) { const double nr = sqrt(s); lamv[r] = nr; invn[r] = nr > 0.0 ? 1.0 / nr : 0.0; }
+  }
   __syncthreads();
   if (tid < FS_M) {
     const double mine = lamv[tid];
@@ -369,8 +496,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   // lambda_m); every kept singular value in the range a single Gram pass resolves (sigma >= 1e-3 sigma_max)
   ok = lamm > 0.0 && resid2 <= 1e-24 * lamm * lamm && tau <= 0.25 * lamm && lamm >= 1e-6 * lam1 && sweeps < 30;
   if (!ok) { fail(); return; }
-  // U = W^T Q (rows in rank order) -> rows 0 .. m-1 of the warm buffer
-  fs_gemm_ab(Wm, ord, A1, warp, lane, [&](int i, int j, double v) { vt[(size_t)i * FS_N + j] = v; });
+  // U = W^T Q (unit rows of Sm in rank order) -> rows 0 .. m-1 of the warm buffer
+  fs_gemm_ab(Sm, ord, A1, warp, lane, [&](int i, int j, double v) { vt[(size_t)i * FS_N + j] = v * invn[ord[i]]; });
   const double tail_mean = fmax(tau, 0.0) / (double)(FS_N - FS_M);
   if (tid < FS_M) {
     lam[tid] = lamv[ord[tid]];
@@ -384,6 +511,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     sub[1] = FS_M;
     if (info) info[0] = (double)(100 + sweeps);        // 100 + sweeps marks a fast-path split in the history
   }
+  tick();                                              // 9: output
 }
 
 // Off the critical path (tail stream), after a successful fast split: rows m..n-1 of the warm buffer still hold the
@@ -396,7 +524,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
   double* Sm = fsm + FS_OFF_S;
   double* Wm = fsm + FS_OFF_W;
   double* misc = fsm + FS_OFF_MISC;
-  double *dinv = misc, *lcol = misc + 64;
+  double *dsave = misc, *yrow = misc + 128, *scol = misc + 592;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (skip[2] == 0.0) return;                          // the ordinary pipeline ran: the buffer holds its full rotation
   for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) {
@@ -417,11 +545,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
   for (int round = 0; round < 2; ++round) {
     fs_gemm_abt(src, src, Wm, warp, lane);             // S = P P^T
     __syncthreads();
-    if (!fs_cholesky(Wm, dinv, lcol, tid)) {
+    if (!fs_orthonormalize(Wm, src, dst, yrow, scol, dsave, tid)) {   // P <- D^-1/2 L^-1 P
       if (tid == 0) skip[1] = 1.0;
       return;
     }
-    fs_forward_subst(Wm, dinv, src, dst, tid);         // P <- L^-1 P
     __syncthreads();
     double* t = src; src = dst; dst = t;
   }
