@@ -41,7 +41,10 @@ extern "C" {
 typedef void* tnml_stream_t; /* cudaStream_t */
 
 enum { TNML_F64 = 0, TNML_F32 = 1 };
-enum { TNML_ACT_LINEAR = 0, TNML_ACT_SIGMOID = 1, TNML_ACT_SOFTMAX = 2 };          /* NC:127 */
+/* TNML_ACT_SOFTMAX is the reference's softmax, NOT max-stabilised (NC:794: exp(f/T) overflows to inf/inf = nan for
+ * |f|/T > ~709); TNML_ACT_SOFTMAX_STABLE is the opt-in exp((f - max f)/T) / sum form: identical where the reference
+ * is finite, finite everywhere. */
+enum { TNML_ACT_LINEAR = 0, TNML_ACT_SIGMOID = 1, TNML_ACT_SOFTMAX = 2, TNML_ACT_SOFTMAX_STABLE = 3 };   /* NC:127 */
 enum { TNML_LOSS_MSE = 0, TNML_LOSS_CROSS_ENTROPY = 1, TNML_LOSS_FULL_CROSS_ENT = 2 }; /* NC:132 */
 enum {
   TNML_OK = 0,

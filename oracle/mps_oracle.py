@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 
-ACT_FNS = ("linear", "sigmoid", "softmax")            # NC:127
+ACT_FNS = ("linear", "sigmoid", "softmax", "softmax_stable")   # NC:127; 'softmax_stable' = opt-in extension
 LOSS_FNS = ("MSE", "cross_entropy", "full_cross_ent")  # NC:132
 
 
@@ -109,6 +109,9 @@ def apply_act(f: np.ndarray, act_fn: str, T: float) -> np.ndarray:
     if act_fn == "softmax":
         e = np.exp(f / T)
         return e / e.sum(axis=1, keepdims=True)                            # NC:794
+    if act_fn == "softmax_stable":      # opt-in: NC:794 with the largest logit subtracted (same value, no overflow)
+        e = np.exp((f - f.max(axis=1, keepdims=True)) / T)
+        return e / e.sum(axis=1, keepdims=True)
     raise AssertionError(act_fn)
 
 
@@ -117,7 +120,7 @@ def loss_derivative(fa: np.ndarray, y1h: np.ndarray, act_fn: str, loss_fn: str, 
     if loss_fn == "MSE":
         return y1h - fa                                                    # NC:824
     if loss_fn == "cross_entropy":
-        if act_fn == "softmax":
+        if act_fn in ("softmax", "softmax_stable"):
             return (y1h - y1h * fa) / T                                    # NC:828
         return y1h / fa                                                    # NC:830
     if loss_fn == "full_cross_ent":
@@ -229,6 +232,16 @@ def choose_m(rule: str, left_dir: bool, pos_l: int, S_sites: int, Dl: int, nS: i
         return nS
 
 
+def adaptive_m(S: np.ndarray, threshold: float, min_bond: int, max_bond: int) -> int:
+    """Opt-in adaptive bond (the authors' unfinished feature): NC:890-891 computes
+    ``index = argmax(cumsum(S)/S.sum() > threshold)`` and never uses it; the intent is in the reference's
+    old_files/TensorNetwork.py:1310-1326, ``m_new = max(10, min(index, m))``.  Restated with the two constants as
+    parameters: m = max(min_bond, min(index, max_bond)), never more than len(S)."""
+    cve = np.cumsum(S) / S.sum()
+    index = int(np.argmax(cve > threshold))
+    return int(min(len(S), max(int(min_bond), min(index, int(max_bond)))))
+
+
 def svd_split(B, left_dir: bool, m: int):
     """Split B[a,s,l,t,c] into the two new sites with sqrt(S) on both factors (NC:887, NC:912-925, NC:947-960).
 
@@ -260,7 +273,7 @@ class OracleMPS:
     """State machine mirroring ``Network`` (NC:10) on canonical arrays.  Records per-step history."""
 
     def __init__(self, sites, L, T=0.1, act_fn="linear", loss_fn="cross_entropy",
-                 rule="reference", max_bond=None, l_pos=0):
+                 rule="reference", max_bond=None, l_pos=0, threshold=0.999, min_bond=2):
         assert act_fn in ACT_FNS and loss_fn in LOSS_FNS
         self.sites = [np.array(s, dtype=np.float64) for s in sites]
         self.S = len(sites)
@@ -268,6 +281,7 @@ class OracleMPS:
         self.T = T
         self.act_fn, self.loss_fn = act_fn, loss_fn
         self.rule, self.max_bond = rule, max_bond
+        self.threshold, self.min_bond = threshold, min_bond
         self.l_pos = l_pos
         self.phi = None
         self.env = None          # env[p]: left env of sites < p (valid p <= l_pos side) or right env of sites >= p
@@ -385,7 +399,11 @@ class OracleMPS:
         a, c = B.shape[0], B.shape[4]
         R_, C_ = (a * 2, self.L * 2 * c) if not left_dir else (a * 2 * self.L, 2 * c)
         nS = min(R_, C_)
-        m = choose_m(self.rule, left_dir, l, S, a, nS, R_, C_, self.max_bond)
+        if self.rule == "adaptive":
+            Mx = Bn.reshape(R_, C_)
+            m = adaptive_m(np.linalg.svd(Mx, compute_uv=False), self.threshold, self.min_bond, self.max_bond)
+        else:
+            m = choose_m(self.rule, left_dir, l, S, a, nS, R_, C_, self.max_bond)
         A_left, A_right, Svals = svd_split(Bn, left_dir, m)                   # NC:563
         if not left_dir:
             self.sites[p] = A_left                                            # (a,s,m)

@@ -9,6 +9,11 @@ B200 through libtnml.so (see ``engine.SweepEngine``).  Additive keyword-only ext
                                                  min(len(S), max_bond) and cuts both factors.
   device, process_group                          CUDA device; torch.distributed group for sample sharding (each rank
                                                  feeds its own shard of the batch, dB and the metrics are all-reduced).
+  truncation='adaptive', threshold=, min_bond=   opt-in: the authors' unfinished adaptive bond (NC:890-891, intent in
+                                                 old_files/TensorNetwork.py:1310-1326): m = max(min_bond, min(index,
+                                                 max_bond)), index = argmax(cumsum(S)/sum(S) > threshold)
+  stable_softmax=True                            opt-in: act_fn='softmax' with the largest logit subtracted before exp
+                                                 (NC:794 overflows to nan for |f|/T > 709); same values where finite
   svd_refine                                     second Jacobi pass (default on; full accuracy for small sing. values)
   dtype='float64' | 'float32'                    per-sample arrays and contractions: FP64 (DMMA, the parity path) or FP32
                                                  storage with TF32 tensor-core products on tcgen05 (bond-tensor algebra
@@ -55,7 +60,8 @@ class Network():
 
     def __init__(self, N, M, D=2, L=10, T=0.1, normalize=False, calibration_X=None, act_fn='linear',
                  loss_fn='cross_entropy', check=False, *, truncation='reference', max_bond=None, device=None,
-                 process_group=None, svd_refine=True, dtype='float64'):
+                 process_group=None, svd_refine=True, dtype='float64', threshold=0.999, min_bond=2,
+                 stable_softmax=False):
         self.N, self.D, self.L, self.M, self.T = N, D, L, M, T
         if D != 2:
             raise NotImplementedError("the device kernels are written for the 2-component feature map (D=2)")
@@ -65,7 +71,8 @@ class Network():
         self.l_pos = 0
         if dtype not in ('float64', 'float32'):
             raise ValueError("dtype must be 'float64' or 'float32'")
-        self._opts = dict(truncation=truncation, max_bond=max_bond, svd_refine=bool(svd_refine), dtype=dtype)
+        self._opts = dict(truncation=truncation, max_bond=max_bond, svd_refine=bool(svd_refine), dtype=dtype,
+                          threshold=threshold, min_bond=min_bond, stable_softmax=bool(stable_softmax))
         self._device, self._group = device, process_group
         self._eng = None
         self._host_As = None          # list[Tensor]; authoritative when _host_fresh
@@ -113,13 +120,17 @@ class Network():
             m = global_abs_max(m, eng.device, group=eng.group, world=eng.world)
         return m
 
+    def _act_name(self):
+        return 'softmax_stable' if (self.act_fn == 'softmax' and self._opts.get("stable_softmax", False)) else self.act_fn
+
     def _engine(self):
         if self._eng is None:
             from .engine import SweepEngine
-            self._eng = SweepEngine(self.N, self.L, self.T, self.act_fn, self.loss_fn,
+            self._eng = SweepEngine(self.N, self.L, self.T, self._act_name(), self.loss_fn,
                                     rule=self._opts["truncation"], max_bond=self._opts["max_bond"],
                                     device=self._device, group=self._group, svd_refine=self._opts["svd_refine"],
-                                    dtype=self._opts.get("dtype", "float64"))
+                                    dtype=self._opts.get("dtype", "float64"),
+                                    threshold=self._opts.get("threshold", 0.999), min_bond=self._opts.get("min_bond", 2))
             self._upload()
         elif self._host_fresh and self._host_dirty:
             self._upload()
@@ -166,28 +177,128 @@ class Network():
         self._last_f = out
         return out
 
+    def register_input(self, X):
+        """Opt-in: page-lock the caller's (batch, N, 2) float64 array in place; forward(X) then copies straight from it.
+        The array is kept alive by the registry; do not modify it while a forward(X) is in flight."""
+        return self._engine().register_input(X)
+
+    # ------------------------------------------------------------------ evaluation without host round trips
+    def evaluate(self, X, y):
+        """Accuracy and MAE of the network on (X, y) -- forward + apply_act_func + accuracy of the reference's test
+        scripts (test_diagonals.py:69-78) in one device-resident pass: only three sums come back to the host.  X:
+        (batch, N, 2) host array or CUDA tensor; y: integer labels.  MAE is against the one-hot target (NC:702)."""
+        eng = self._engine()
+        eng.load_input(X)
+        eng.forward()
+        eng.set_labels(y)
+        self._last_f = None
+        return eng.eval_metrics()
+
     # ------------------------------------------------------------------ train (NC:261-350)
+    def _resident(self, loader):
+        """(data, labels) of the loader's dataset on the device, uploaded ONCE, when the dataset is array-backed
+        (``.data`` of shape (n, N, 2) and ``.label``, like data_generator.NumpyDataset); None otherwise."""
+        ds = getattr(loader, "dataset", None)
+        data, label = getattr(ds, "data", None), getattr(ds, "label", None)
+        if (data is None or label is None or getattr(loader, "batch_sampler", None) is None
+                or getattr(loader, "num_workers", 0) != 0):
+            return None
+        data = np.asarray(data)
+        if data.ndim != 3 or data.shape[1] != self.N or data.shape[2] != 2:
+            return None
+        import torch
+        cache = self.__dict__.setdefault("_resident_cache", {})
+        hit = cache.get(id(ds))
+        if hit is None or hit[0] is not ds:
+            dev = self._engine().device
+            hit = (ds, torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(dev),
+                   torch.from_numpy(np.ascontiguousarray(np.asarray(label), dtype=np.int32)).to(dev))
+            cache.clear()
+            cache[id(ds)] = hit
+        return hit[1], hit[2]
+
+    @staticmethod
+    def _index_batches(loader):
+        """The loader's batches as index arrays, with exactly the RNG consumption of iterating the loader itself (the
+        iterator's base seed first, then the sampler's draws), without touching the samples.  SubsetRandomSampler and
+        SequentialSampler under a plain BatchSampler (what data_generator.prepare_dataset builds, DG:187-192) are
+        evaluated vectorised -- iterating a 60 000-index sampler element by element costs more than a sweep; any
+        other sampler is iterated through an index-only DataLoader."""
+        import torch
+        from torch.utils.data import BatchSampler, DataLoader, SequentialSampler, SubsetRandomSampler
+        bs, smp = loader.batch_sampler, getattr(loader, "sampler", None)
+        if type(bs) is BatchSampler and type(smp) in (SubsetRandomSampler, SequentialSampler):
+            def fast():
+                torch.empty((), dtype=torch.int64).random_(generator=loader.generator)   # the iterator's base seed
+                if type(smp) is SubsetRandomSampler:
+                    perm = torch.randperm(len(smp.indices), generator=smp.generator).numpy()
+                    order = np.asarray(smp.indices)[perm]
+                else:
+                    order = np.arange(len(smp))
+                n, b = len(order), bs.batch_size
+                stop = (n // b) * b if bs.drop_last else n
+                for lo in range(0, stop, b):
+                    yield order[lo:min(lo + b, stop)]
+            return fast()
+
+        class _Indices:
+            def __init__(self, n):
+                self.n = n
+
+            def __len__(self):
+                return self.n
+
+            def __getitem__(self, i):
+                return i
+
+        return DataLoader(_Indices(len(loader.dataset)), batch_sampler=bs, collate_fn=list, generator=loader.generator)
+
     def train(self, train_loader, val_loader, lr, n_epochs=10, weight_dec=0.001, L2_flag=True, debug=False):
+        """NC:261-350.  Loaders over an array-backed dataset (what data_generator.prepare_dataset builds) take the
+        resident path: the dataset is uploaded once, every batch is gathered on the device from the sampler's indices,
+        and nothing but the per-step metrics returns to the host.  Any other loader is collated on the host like the
+        reference does (NC:324-325)."""
+        import torch
         val_acc, var_hist = [], []
         print("\n --- TRAINING PROCEDURE ---")
+        res_train, res_val = self._resident(train_loader), self._resident(val_loader)
         for epoch in range(n_epochs):
             epoch_train_acc = np.zeros(len(train_loader))
             var_hist.append([[] for _ in range(7)] if debug else [[], []])
-            for i, data in enumerate(train_loader, 0):
-                x = np.array([s[0] for s in data])
-                y = np.array([s[1] for s in data])
-                f = self.forward(x)
-                epoch_train_acc[i] = self.accuracy(x, y, f)          # accuracy before the batch optimisation
-                left_dir = (self.l_pos == self.N - 1)
-                f = self.sweep(x, y, f, lr, weight_dec, L2_flag=L2_flag, left_dir=left_dir, var_hist=var_hist[epoch],
-                               debug=debug)
+            batches = self._index_batches(train_loader) if res_train is not None else train_loader
+            for i, data in enumerate(batches, 0):
+                if res_train is not None:
+                    eng = self._engine()
+                    idx = torch.as_tensor(np.asarray(data), dtype=torch.long, device=eng.device)
+                    eng.load_input(res_train[0].index_select(0, idx))
+                    eng.forward()
+                    self._last_f = None
+                    left_dir = (self.l_pos == self.N - 1)
+                    eng.begin_sweep(res_train[1].index_select(0, idx), left_dir, L2_flag)
+                    epoch_train_acc[i] = eng.first_step_accuracy(left_dir)   # accuracy before the batch optimisation
+                    for _ in range(self.N - 1):
+                        eng.sweep_step(lr, weight_dec, L2_flag, left_dir)
+                    self._after_steps(var_hist[epoch], debug, L2_flag)
+                else:
+                    x = np.array([s[0] for s in data])
+                    y = np.array([s[1] for s in data])
+                    f = self.forward(x)
+                    epoch_train_acc[i] = self.accuracy(x, y, f)          # accuracy before the batch optimisation
+                    left_dir = (self.l_pos == self.N - 1)
+                    f = self.sweep(x, y, f, lr, weight_dec, L2_flag=L2_flag, left_dir=left_dir, var_hist=var_hist[epoch],
+                                   debug=debug)
                 print('\r' + "Epoch %d/%d - train accuracy : %.4f - completed : %.2f " %
                       (epoch, n_epochs, epoch_train_acc[i], (i + 1) * 100 / len(train_loader)) + '%', end=' ')
             epoch_val_acc = np.zeros(len(val_loader))
-            for i, data in enumerate(val_loader, 0):
-                x = np.array([s[0] for s in data])
-                y = np.array([s[1] for s in data])
-                epoch_val_acc[i] = self.accuracy(x, y)
+            batches = self._index_batches(val_loader) if res_val is not None else val_loader
+            for i, data in enumerate(batches, 0):
+                if res_val is not None:
+                    idx = torch.as_tensor(np.asarray(data), dtype=torch.long, device=self._engine().device)
+                    epoch_val_acc[i] = self.evaluate(res_val[0].index_select(0, idx), res_val[1].index_select(0, idx))[0]
+                else:
+                    x = np.array([s[0] for s in data])
+                    y = np.array([s[1] for s in data])
+                    epoch_val_acc[i] = self.accuracy(x, y)
             val_acc.append(epoch_val_acc.mean())
             print('\r' + "Epoch %d/%d - train accuracy : %.4f - val accuracy: %.4f" %
                   (epoch, n_epochs, epoch_train_acc.mean(), val_acc[-1]))
@@ -348,13 +459,13 @@ class Network():
         out = torch.empty_like(dev)
         st = torch.cuda.current_stream(eng.device).cuda_stream
         if kind == "act":
-            _lib.call("tnml_apply_act", dev.data_ptr(), out.data_ptr(), Ns, L, _lib.ACT[self.act_fn], float(self.T),
+            _lib.call("tnml_apply_act", dev.data_ptr(), out.data_ptr(), Ns, L, _lib.ACT[self._act_name()], float(self.T),
                       _lib.F64, st)
         else:
             yb = np.broadcast_to(np.asarray(y, dtype=np.float64), np.asarray(f_elem).shape)
             yd = torch.from_numpy(np.ascontiguousarray(np.moveaxis(yb, label_axis, 0).reshape(L, -1))).to(eng.device)
             _lib.call("tnml_loss_derivative", dev.data_ptr(), yd.data_ptr(), out.data_ptr(), Ns, L,
-                      _lib.ACT[self.act_fn], _lib.LOSS[self.loss_fn], float(self.T), _lib.F64, st)
+                      _lib.ACT[self._act_name()], _lib.LOSS[self.loss_fn], float(self.T), _lib.F64, st)
         res = out.cpu().numpy().reshape(moved.shape)
         return np.ascontiguousarray(np.moveaxis(res, 0, label_axis))
 

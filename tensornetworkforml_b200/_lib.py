@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtnml.so")
 
 F64, F32 = 0, 1
-ACT = {"linear": 0, "sigmoid": 1, "softmax": 2}
+ACT = {"linear": 0, "sigmoid": 1, "softmax": 2, "softmax_stable": 3}
 LOSS = {"MSE": 0, "cross_entropy": 1, "full_cross_ent": 2}
 
 # every symbol include/tnml.h declares: name -> (restype, argtypes)
@@ -85,23 +85,47 @@ def lib():
     return _lib
 
 
-_registered = []        # host buffers page-locked in place by this process: [(ptr, nbytes)], most recent last
+class _Registration:
+    """One host buffer page-locked in place.  Holds a STRONG reference to the array, so the memory cannot be freed (and
+    its address re-used by another allocation) while the driver still has it mapped."""
+    __slots__ = ("arr", "ptr", "nbytes")
+
+    def __init__(self, arr):
+        self.arr, self.ptr, self.nbytes = arr, arr.ctypes.data, arr.nbytes
 
 
-def host_register(ptr: int, nbytes: int, keep: int = 3) -> bool:
-    """Page-lock [ptr, ptr+nbytes) once (process-wide LRU of ``keep`` buffers).  False if the driver refuses."""
-    key = (ptr, nbytes)
-    if key in _registered:
-        _registered.remove(key)
-        _registered.append(key)
-        return True
+_registered = []        # explicit registrations of this process, most recent last
+
+
+def register_host_array(arr, keep: int = 3) -> bool:
+    """Page-lock the NumPy array ``arr`` in place (cudaHostRegister) so that host->device copies DMA straight from it.
+    Opt-in: only arrays the caller hands over explicitly are registered, the registry keeps them alive, and the oldest
+    registration is released (cudaHostUnregister) when more than ``keep`` are held.  Returns False when the driver
+    refuses -- including 'already registered' for a range this registry does not own."""
+    for i, r in enumerate(_registered):
+        if r.arr is arr:
+            _registered.append(_registered.pop(i))
+            return True
     while len(_registered) >= keep:
-        old_ptr, _ = _registered.pop(0)
-        lib().tnml_host_unregister(old_ptr)
-    rc = lib().tnml_host_register(ptr, nbytes)
-    if rc == 0:
-        _registered.append(key)
-    return rc in (0, 1)
+        unregister_host_array(_registered[0].arr)
+    reg = _Registration(arr)
+    if lib().tnml_host_register(reg.ptr, reg.nbytes) != 0:
+        return False
+    _registered.append(reg)
+    return True
+
+
+def unregister_host_array(arr) -> None:
+    for i, r in enumerate(_registered):
+        if r.arr is arr:
+            lib().tnml_host_unregister(r.ptr)
+            _registered.pop(i)
+            return
+
+
+def is_registered(arr) -> bool:
+    """True when exactly this array object (same memory, still alive by construction) is page-locked by this registry."""
+    return any(r.arr is arr for r in _registered)
 
 
 def check(rc: int, what: str = ""):

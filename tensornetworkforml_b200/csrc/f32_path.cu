@@ -147,10 +147,15 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
   if (b < Ns) {
     const float* fb = f + b * L;
     const int yb = y[b];
-    double denom = 1.0;
-    if (act == TNML_ACT_SOFTMAX) {
+    double denom = 1.0, shift = 0.0;
+    const bool softmax = act == TNML_ACT_SOFTMAX || act == TNML_ACT_SOFTMAX_STABLE;
+    if (act == TNML_ACT_SOFTMAX_STABLE) {
+      shift = fb[0];
+      for (int l = 1; l < L; ++l) shift = fmax(shift, (double)fb[l]);
+    }
+    if (softmax) {
       denom = 0.0;
-      for (int l = 0; l < L; ++l) denom += exp((double)fb[l] / T);
+      for (int l = 0; l < L; ++l) denom += exp(((double)fb[l] - shift) / T);
     }
     const float2 p = phi_p[b], r = phi_q[b];
     const float4 w = make_float4(p.x * r.x, p.x * r.y, p.y * r.x, p.y * r.y);
@@ -161,13 +166,13 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
       double fa;
       if (act == TNML_ACT_LINEAR) fa = v;
       else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));
-      else fa = exp(v / T) / denom;
+      else fa = exp((v - shift) / T) / denom;
       if (l == 0 || fa > best) { best = fa; arg = l; }
       const double yl = (l == yb) ? 1.0 : 0.0;
       abs_err += fabs(yl - fa);
       double gv;
       if (loss == TNML_LOSS_MSE) gv = yl - fa;
-      else if (loss == TNML_LOSS_CROSS_ENTROPY) gv = (act == TNML_ACT_SOFTMAX) ? (yl - yl * fa) / T : yl / fa;
+      else if (loss == TNML_LOSS_CROSS_ENTROPY) gv = softmax ? (yl - yl * fa) / T : yl / fa;
       else gv = 1.0 / ((l == yb ? fa : fa - 1.0) + 1e-4);
       g[b * L + l] = (float)gv;
     }

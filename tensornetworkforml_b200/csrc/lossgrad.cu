@@ -22,10 +22,15 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
   if (b < Ns) {
     const double* fb = f + b * L;
     const int yb = y[b];
-    double denom = 1.0;
-    if (act == TNML_ACT_SOFTMAX) {  // NC:794 -- NOT max-stabilised, exactly like the reference
+    double denom = 1.0, shift = 0.0;
+    const bool softmax = act == TNML_ACT_SOFTMAX || act == TNML_ACT_SOFTMAX_STABLE;
+    if (act == TNML_ACT_SOFTMAX_STABLE) {   // opt-in: subtract the largest logit (exact in infinite precision)
+      shift = fb[0];
+      for (int l = 1; l < L; ++l) shift = fmax(shift, fb[l]);
+    }
+    if (softmax) {  // NC:794 -- TNML_ACT_SOFTMAX is NOT max-stabilised, exactly like the reference
       denom = 0.0;
-      for (int l = 0; l < L; ++l) denom += exp(fb[l] / T);
+      for (int l = 0; l < L; ++l) denom += exp((fb[l] - shift) / T);
     }
     const double2 p = phi_p[b], r = phi_q[b];
     const double w0 = p.x * r.x, w1 = p.x * r.y, w2 = p.y * r.x, w3 = p.y * r.y;
@@ -35,14 +40,14 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
       double v = fb[l], fa;
       if (act == TNML_ACT_LINEAR) fa = v;
       else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));  // NC:791
-      else fa = exp(v / T) / denom;
+      else fa = exp((v - shift) / T) / denom;
       if (l == 0 || fa > best) { best = fa; arg = l; }  // np.argmax: first maximum
       const double yl = (l == yb) ? 1.0 : 0.0;
       abs_err += fabs(yl - fa);
       double g;
       if (loss == TNML_LOSS_MSE) g = yl - fa;  // NC:824
       else if (loss == TNML_LOSS_CROSS_ENTROPY)
-        g = (act == TNML_ACT_SOFTMAX) ? (yl - yl * fa) / T : yl / fa;  // NC:828, NC:830
+        g = softmax ? (yl - yl * fa) / T : yl / fa;  // NC:828, NC:830
       else g = 1.0 / ((l == yb ? fa : fa - 1.0) + 1e-4);               // NC:832-833
       double* qo = q + (b * L + l) * 4;
       qo[0] = g * w0; qo[1] = g * w1; qo[2] = g * w2; qo[3] = g * w3;
@@ -72,17 +77,21 @@ __global__ void __launch_bounds__(256) k_apply_act(const double* __restrict__ f,
                                                    int L, int act, double T) {
   const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (b >= Ns) return;
-  double denom = 1.0;
-  if (act == TNML_ACT_SOFTMAX) {
+  double denom = 1.0, shift = 0.0;
+  if (act == TNML_ACT_SOFTMAX_STABLE) {
+    shift = f[b];
+    for (int l = 1; l < L; ++l) shift = fmax(shift, f[(int64_t)l * Ns + b]);
+  }
+  if (act == TNML_ACT_SOFTMAX || act == TNML_ACT_SOFTMAX_STABLE) {
     denom = 0.0;
-    for (int l = 0; l < L; ++l) denom += exp(f[(int64_t)l * Ns + b] / T);
+    for (int l = 0; l < L; ++l) denom += exp((f[(int64_t)l * Ns + b] - shift) / T);
   }
   for (int l = 0; l < L; ++l) {
     const double v = f[(int64_t)l * Ns + b];
     double fa;
     if (act == TNML_ACT_LINEAR) fa = v;
     else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));
-    else fa = exp(v / T) / denom;
+    else fa = exp((v - shift) / T) / denom;
     out[(int64_t)l * Ns + b] = fa;
   }
 }
@@ -95,7 +104,8 @@ __global__ void __launch_bounds__(256) k_loss_der(const double* __restrict__ fa,
   const double f = fa[e], yy = y[e];
   double g;
   if (loss == TNML_LOSS_MSE) g = yy - f;
-  else if (loss == TNML_LOSS_CROSS_ENTROPY) g = (act == TNML_ACT_SOFTMAX) ? (yy - yy * f) / T : yy / f;
+  else if (loss == TNML_LOSS_CROSS_ENTROPY)
+    g = (act == TNML_ACT_SOFTMAX || act == TNML_ACT_SOFTMAX_STABLE) ? (yy - yy * f) / T : yy / f;
   else g = 1.0 / ((yy == 0.0 ? f - 1.0 : f) + 1e-4);
   out[e] = g;
 }
@@ -270,7 +280,7 @@ extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi
                                 int32_t dtype, tnml_stream_t stream) {
   TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);
   TNML_REQUIRE(f && y && phi_p && phi_q && q && pp && metrics && ws && Ns > 0 && L > 0 && L <= AL_MAXL);
-  TNML_REQUIRE(act >= 0 && act <= 2 && loss >= 0 && loss <= 2);
+  TNML_REQUIRE(act >= 0 && act <= 3 && loss >= 0 && loss <= 2);
   if (dtype == TNML_F32)
     return f32::act_lossder((const float*)f, y, (const float*)phi_p, (const float*)phi_q, (float*)q, (float*)pp,
                             (double*)metrics, (double*)ws, Ns, L, act, loss, T, (cudaStream_t)stream);
@@ -287,7 +297,7 @@ extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi
 extern "C" int tnml_apply_act(const void* f, void* out, int64_t Ns, int32_t L, int32_t act, double T, int32_t dtype,
                               tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
-  TNML_REQUIRE(f && out && Ns > 0 && L > 0 && act >= 0 && act <= 2);
+  TNML_REQUIRE(f && out && Ns > 0 && L > 0 && act >= 0 && act <= 3);
   TNML_COUNT(1);
   k_apply_act<<<tnml_cdiv(Ns, 256), 256, 0, (cudaStream_t)stream>>>((const double*)f, (double*)out, Ns, L, act, T);
   return tnml_launch_status();
@@ -296,7 +306,7 @@ extern "C" int tnml_apply_act(const void* f, void* out, int64_t Ns, int32_t L, i
 extern "C" int tnml_loss_derivative(const void* fa, const void* y, void* out, int64_t Ns, int32_t L, int32_t act,
                                     int32_t loss, double T, int32_t dtype, tnml_stream_t stream) {
   TNML_F64_ONLY(dtype);
-  TNML_REQUIRE(fa && y && out && Ns > 0 && L > 0 && act >= 0 && act <= 2 && loss >= 0 && loss <= 2);
+  TNML_REQUIRE(fa && y && out && Ns > 0 && L > 0 && act >= 0 && act <= 3 && loss >= 0 && loss <= 2);
   TNML_COUNT(1);
   k_loss_der<<<tnml_cdiv(Ns * L, 256), 256, 0, (cudaStream_t)stream>>>((const double*)fa, (const double*)y, (double*)out,
                                                                       Ns * L, act, loss, T);

@@ -30,7 +30,7 @@ def choose_m(rule, max_bond, left_dir, l_pos, S, Dl, R, C):
     """Bond kept by the SVD split.  'fixed': min(len(S), max_bond).  'reference': NC:898-910 / NC:933-945 -- the left
     bond of the pair in the interior, len(S) at the chain ends; raises where the reference's np.dot would."""
     nS = min(R, C)
-    if rule == "fixed":
+    if rule in ("fixed", "adaptive"):          # adaptive: the cap; the data-dependent cut follows the split
         return min(nS, max_bond)
     if not left_dir:
         if l_pos == 0:
@@ -78,14 +78,17 @@ class _Timed:
 
 class SweepEngine:
     def __init__(self, S, L, T=0.1, act_fn="linear", loss_fn="cross_entropy", rule="reference", max_bond=None,
-                 device=None, group=None, svd_refine=True, dtype="float64"):
+                 device=None, group=None, svd_refine=True, dtype="float64", threshold=0.999, min_bond=2):
         if not torch.cuda.is_available():
             raise RuntimeError("tensornetworkforml_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         _lib.lib()
-        if rule not in ("reference", "fixed"):
-            raise ValueError("truncation rule must be 'reference' or 'fixed'")
-        if rule == "fixed" and not max_bond:
-            raise ValueError("rule='fixed' needs max_bond")
+        if rule not in ("reference", "fixed", "adaptive"):
+            raise ValueError("truncation rule must be 'reference', 'fixed' or 'adaptive'")
+        if rule in ("fixed", "adaptive") and not max_bond:
+            raise ValueError("rule='%s' needs max_bond" % rule)
+        # 'adaptive' (opt-in, NC:890-891 + old_files/TensorNetwork.py:1310-1326): the bond kept depends on the singular
+        # values, so every split reads them back (one host synchronisation per bond update)
+        self.threshold, self.min_bond = float(threshold), int(min_bond)
         self.S, self.L, self.T = int(S), int(L), float(T)
         self.act, self.loss = ACT[act_fn], LOSS[loss_fn]
         self.rule, self.max_bond = rule, (int(max_bond) if max_bond else None)
@@ -117,6 +120,7 @@ class SweepEngine:
         self.y_dev = None
         self.hist = None
         self._pinned = None
+        self._pin_evt = None
         self._ws = {}
         self.timers = None            # dict name -> [(event0, event1, flops)] when bench.py switches timing on
         self.overlap_svd = True       # SVD split on a side stream, concurrent with the projection
@@ -163,9 +167,13 @@ class SweepEngine:
             self._ws_cache[key] = v
         return v
 
-    def _host_register(self, arr):
-        """Page-lock the NumPy buffer in place (process-wide registry in _lib, survives engine re-creation)."""
-        return _lib.host_register(arr.ctypes.data, arr.nbytes)
+    def register_input(self, X):
+        """Opt-in: page-lock the caller's (Ns, S, 2) float64 C-contiguous array in place.  load_input() then copies
+        straight from it (no staging copy); the registry keeps the array alive until it is evicted or unregistered.  The
+        caller must not modify X while a load_input(X) is in flight."""
+        if not (isinstance(X, np.ndarray) and X.dtype == np.float64 and X.flags["C_CONTIGUOUS"]):
+            raise ValueError("register_input needs a C-contiguous float64 ndarray")
+        return _lib.register_host_array(X)
 
     def _side_stream(self):
         if self._side is None:
@@ -284,20 +292,28 @@ class SweepEngine:
             Xd = X.to(torch.float64).contiguous()
             Ns = Xd.shape[0]
         else:
-            X = np.ascontiguousarray(X, dtype=np.float64)
-            Ns = X.shape[0]
-            Xh = torch.from_numpy(X).reshape(-1)
+            direct = isinstance(X, np.ndarray) and _lib.is_registered(X)   # register_input(X): page-locked in place
+            Xc = np.ascontiguousarray(X, dtype=np.float64)                  # (X itself when it already has this form)
+            Ns = Xc.shape[0]
+            Xh = torch.from_numpy(Xc).reshape(-1)
             Xd = self._workspace("xstage", Xh.numel() * 8)[:Xh.numel()]
-            if Xh.numel() * 8 >= (8 << 20) and self._host_register(X):
-                # the caller's buffer is page-locked in place (cached by address): the DMA engine reads it directly,
-                # no pageable -> pinned staging copy (which cost ~100 ms for the 188 MB batch of config 3)
+            if direct:
+                # the DMA engine reads the caller's buffer directly: no pageable -> pinned staging copy (which cost
+                # ~100 ms for the 188 MB batch of config 3)
                 Xd.copy_(Xh, non_blocking=True)
             else:
+                # owned page-locked staging buffer; the previous transfer out of it must have finished before the host
+                # overwrites it
+                if self._pin_evt is not None:
+                    self._pin_evt.synchronize()
                 if self._pinned is None or self._pinned.numel() < Xh.numel():
                     self._pinned = torch.empty(Xh.numel(), dtype=torch.float64).pin_memory()
                 pin = self._pinned[:Xh.numel()]
                 pin.copy_(Xh)
                 Xd.copy_(pin, non_blocking=True)
+                if self._pin_evt is None:
+                    self._pin_evt = torch.cuda.Event()
+                self._pin_evt.record(torch.cuda.current_stream(self.device))
         assert Xd.numel() == Ns * self.S * 2, "input must have shape (Ns, S, 2)"
         self._ald_for = None
         self._alloc_batch(Ns)
@@ -309,6 +325,7 @@ class SweepEngine:
         xd = x if (isinstance(x, torch.Tensor) and x.is_cuda) else torch.from_numpy(
             np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
         Ns = xd.shape[0]
+        self._ald_for = None
         self._alloc_batch(Ns)
         call("tnml_feature_map", _ptr(xd.contiguous()), _ptr(self.phi), Ns, self.S, self.DT, self._stream())
 
@@ -428,6 +445,38 @@ class SweepEngine:
         self.hist["tail_recs"][:, 1] = 1.0            # "nothing recorded" until a tail call writes the header
         self._st = None
 
+    def _metrics_now(self, p, q, keep_for=None):
+        """Accuracy and MAE of the current prediction against the labels (NC:354-380, NC:697-702): the activation /
+        loss-derivative kernel's metric sums, all-reduced over the sample shards; one 32-byte device->host read."""
+        self._enter()
+        gb = self._workspace("gbuf", 8 * 8)
+        met = gb[gb.numel() - 4:]
+        if keep_for is not None:
+            # the first bond update of the sweep reuses q, pp and these sums (they sit where update_phase expects them)
+            Dl, Dr = self.bonds[p], self.bonds[q + 1]
+            nB = Dl * 4 * self.L * Dr
+            gb = self._workspace("gbuf", (nB + 4) * 8)
+            met = gb[nB:nB + 4]
+        self._act_lossder(p, q, met)
+        self._ald_for = keep_for
+        self._st = None
+        m = met.clone()
+        if self.world > 1:
+            torch.distributed.all_reduce(m[:3], group=self.group)
+        m = m.cpu().numpy()
+        return float(m[0] / m[2]), float(m[1] / (m[2] * self.L))
+
+    def eval_metrics(self):
+        """(accuracy, MAE) of the prediction left by forward() for the labels given to set_labels()."""
+        p = min(self.l_pos, self.S - 2)
+        return self._metrics_now(p, p + 1)
+
+    def first_step_accuracy(self, left_dir):
+        """Accuracy of the prediction a sweep starts from (what Network.train prints before the batch optimisation,
+        NC:328); call between begin_sweep and the first sweep_step."""
+        p = self.l_pos - 1 if left_dir else self.l_pos
+        return self._metrics_now(p, p + 1, keep_for=(p, left_dir))[0]
+
     def sweep_step(self, lr, weight_dec, L2_flag, left_dir):
         """One bond update (NC:440-573 with update_B NC:577-763); everything stays on the device."""
         ctx = self.update_phase(lr, weight_dec, L2_flag, left_dir)
@@ -450,6 +499,9 @@ class SweepEngine:
         q = p + 1
         if (not left_dir and not (0 <= l <= S - 2)) or (left_dir and not (1 <= l <= S - 1)):
             raise Exception("l = %d -> position not allowed for %s sweep step" % (l, "left" if left_dir else "right"))
+        # the label site may have been switched to the other layout since begin_sweep (get_sites(), i.e. reading
+        # Network.As or pickling between two steps of the public per-step API)
+        self._label_to("L" if left_dir else "R")
         step = self.hist["n"]
         side = self._side_stream() if self.overlap_svd else main
         Dl, Dm, Dr = self.bonds[p], self.bonds[q], self.bonds[q + 1]
@@ -496,8 +548,10 @@ class SweepEngine:
         with _Timed(self, "grad", 8.0 * Ns * L * Dl * Dr):
             call("tnml_grad", _ptr(self.q_buf), self._env(p), self._env(q + 1), _ptr(dB), _ptr(ws), Ns, Dl, Dr, L,
                  self.DT, st)
-        reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world,   # one collective per update
-                                    count_written=True)
+        if self.world > 1:
+            with _Timed(self, "allreduce", 0.0):
+                reduce_gradient_and_metrics(gbuf, nB, Ns, group=self.group, world=self.world,   # one collective per update
+                                            count_written=True)
         call("tnml_copy", self.hist["metrics"].data_ptr() + step * 32, _ptr(met), 32, st)
         # regularisation, clipping, update                                                   NC:728-761
         if side is not main:
@@ -518,7 +572,8 @@ class SweepEngine:
         m = self._choose_m(left_dir, Dl, R, Cc)
         new_p = self._empty(Dl * 2 * m * (L if left_dir else 1))
         new_q = self._empty(m * 2 * Dr * (1 if left_dir else L))
-        defer = bool(self.defer_tail and self.svd_refine == 1 and side is not main)
+        adaptive = self.rule == "adaptive"
+        defer = bool(self.defer_tail and self.svd_refine == 1 and side is not main and not adaptive)
         par = step % self.n_svd_ws
         ws_svd = self._workspace("svd%d" % par, self._ws_bytes("tnml_svd_split_workspace_bytes", Dl, Dr, L,
                                                                1 if left_dir else 0))
@@ -607,6 +662,18 @@ class SweepEngine:
         if side is not main:
             main.wait_stream(side)                      # the next step needs the new site tensors
             self._inflight = ctx                        # keep B, B', G alive until the main stream has passed the wait
+        if adaptive:
+            # m = max(min_bond, min(index, max_bond)) with index = argmax(cumsum(S)/sum(S) > threshold)  (NC:890-891):
+            # the factors were computed for the cap, their leading m columns / rows are the truncated factors
+            main.synchronize()
+            nS = min(R, Cc)
+            sv = self.hist["svals"][step, :nS].cpu().numpy()
+            index = int(np.argmax(np.cumsum(sv) / sv.sum() > self.threshold))
+            m_keep = int(min(nS, max(self.min_bond, min(index, self.max_bond))))
+            if m_keep < m:
+                new_p = new_p.view(-1, m)[:, :m_keep].contiguous().view(-1)
+                new_q = new_q.view(m, -1)[:m_keep].contiguous().view(-1)
+                m = m_keep
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

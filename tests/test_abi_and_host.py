@@ -164,3 +164,32 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["unit"] == "bond-updates/s" and line["config"]["Ns"] == 60000
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_index_batches_reproduce_the_loader_and_its_rng_consumption():
+    """Network.train's resident path asks the loader's sampler for INDICES (DG:187-192): same batches and same torch RNG
+    state afterwards as iterating the loader itself, for the samplers prepare_dataset builds and for a generic one."""
+    import torch
+    from torch.utils.data import DataLoader
+    import tensornetworkforml_b200.data_generator as gen
+    from tensornetworkforml_b200.Network_class import Network
+    np.random.seed(0)
+    data, label = gen.create_dataset(100, 4, 0.7)
+
+    def loaders():
+        torch.manual_seed(0)
+        tl, vl, _ = gen.prepare_dataset(data, label, 1, 0.2, 24, 8, 8)
+        sh = DataLoader(tl.dataset, 16, shuffle=True, collate_fn=lambda b: b)      # RandomSampler: generic path
+        sq = DataLoader(tl.dataset, 30, collate_fn=lambda b: b)                    # SequentialSampler, ragged tail
+        return [tl, vl, sh, sq]
+
+    def position(ds, x):
+        return int(np.where((ds.data == x).all(axis=(1, 2)))[0][0])
+
+    for k in range(4):
+        ld = loaders()[k]
+        real = [[position(ld.dataset, s[0]) for s in b] for b in ld]
+        st_real = torch.get_rng_state()
+        ld = loaders()[k]
+        mine = [[int(i) for i in b] for b in Network._index_batches(ld)]
+        assert mine == real and torch.equal(torch.get_rng_state(), st_real), "loader %d" % k

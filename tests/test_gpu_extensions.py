@@ -1,0 +1,262 @@
+"""GPU: rows (f) of SURVEY.md section 8 and the round-1 advisor findings.
+
+ f1  Network.train keeps an array-backed dataset resident (NC:324-325, DG:190-192): same result as the host collation
+ f2  Network.evaluate: forward + activation + accuracy without host round trips (test_diagonals.py:69-78)
+ f3  opt-ins: adaptive truncation (NC:890-891 + old_files/TensorNetwork.py:1310-1326), max-stabilised softmax (NC:794)
+ ADVICE: label-site layout after reading Network.As between two sweep_step calls; explicit input registration
+Tolerance 1e-10 (FP64) against the oracle unless stated."""
+import contextlib
+import io
+import time
+
+import numpy as np
+import pytest
+
+from oracle import mps_oracle as O
+from tests import _golden as G
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def tn():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import tensornetworkforml_b200 as pkg
+    return pkg
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def _pair(tn, S, D, Lbl, Ns, act, loss, seed, **kw):
+    np.random.seed(seed)
+    X = O.feature_map(np.random.random((Ns, S)))
+    y = np.random.randint(0, Lbl, Ns)
+    state = np.random.get_state()
+    okw = dict(rule=kw.get("truncation", "reference"), max_bond=kw.get("max_bond"))
+    if "threshold" in kw:
+        okw.update(threshold=kw["threshold"], min_bond=kw["min_bond"])
+    oact = "softmax_stable" if kw.get("stable_softmax") else act
+    orc = O.OracleMPS.from_seed(S, D, Lbl, calibration_X=X, normalize=True, act_fn=oact, loss_fn=loss, **okw)
+    np.random.set_state(state)
+    with quiet():
+        net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=X, act_fn=act, loss_fn=loss, **kw)
+    return X, y, orc, net
+
+
+# ------------------------------------------------------------------------------------------- ADVICE (medium)
+def test_reading_As_between_left_sweep_steps_keeps_the_update_right(tn):
+    """get_sites() (the Network.As getter, pickling) switches the label site to the right-sweep layout; the next
+    left-direction sweep_step must switch it back before forming B (NC:484)."""
+    S, D, Lbl, Ns = 8, 6, 3, 96
+    X, y, orc, net = _pair(tn, S, D, Lbl, Ns, "linear", "MSE", 5, truncation="fixed", max_bond=D)
+    fo, f = orc.forward(X), net.forward(X)
+    fo = orc.sweep(y, fo, 0.02, 0.01, True, False)                     # right sweep: label ends at S-1
+    f = net.sweep(X, y, f, 0.02, 0.01, L2_flag=True, left_dir=False)
+    fo, f = orc.forward(X), net.forward(X)
+    y1h = np.eye(Lbl)[y]
+    orc._build_norm_stack(True)
+    for step in range(S - 1):
+        fo = orc.sweep_step(fo, y1h, 0.02, 0.01, True, True)
+        f = net.sweep_step(f, y1h.T, 0.02, Ns, 0.01, L2_flag=True, left_dir=True)
+        assert G.rel(f.elem.T, fo) < TOL, "step %d" % step
+        _ = [np.asarray(T.elem).sum() for T in net.As]                  # read the sites between two steps
+    assert net.l_pos == 0
+
+
+# ------------------------------------------------------------------------------------------- ADVICE (high)
+def test_register_input_is_explicit_and_keeps_the_array_alive(tn):
+    from tensornetworkforml_b200 import _lib
+    S, D, Lbl, Ns = 6, 4, 2, 40000                                      # 3.8 MB: below any implicit threshold of old
+    X, y, orc, net = _pair(tn, S, D, Lbl, Ns, "linear", "MSE", 6)
+    f0 = net.forward(X).elem.copy()
+    assert not _lib.is_registered(X)                                     # nothing is registered behind the caller's back
+    assert net.register_input(X) and _lib.is_registered(X)
+    assert np.array_equal(net.forward(X).elem, f0)                       # direct DMA from the caller's buffer
+    others = [np.ascontiguousarray(X + i) for i in range(1, 4)]
+    for o in others:                                                     # LRU of three: X is evicted and unregistered
+        assert net.register_input(o)
+    assert not _lib.is_registered(X) and all(_lib.is_registered(o) for o in others)
+    assert np.array_equal(net.forward(X).elem, f0)                       # staged path again, same values
+    with pytest.raises(ValueError):
+        net.register_input(X[:, :, ::-1])                                # not contiguous: never registered
+    for o in others:
+        _lib.unregister_host_array(o)
+    assert not any(_lib.is_registered(o) for o in others)
+    # back-to-back loads through the owned staging buffer do not corrupt each other
+    eng = net._engine()
+    eng.load_input(others[0]); eng.load_input(X)
+    assert np.array_equal(eng.forward().cpu().numpy().T, f0)
+
+
+# ------------------------------------------------------------------------------------------- f2
+@pytest.mark.parametrize("act", ["linear", "softmax", "sigmoid"])
+def test_evaluate_equals_forward_act_accuracy(tn, act):
+    S, D, Lbl, Ns = 10, 5, 4, 333
+    X, y, orc, net = _pair(tn, S, D, Lbl, Ns, act, "MSE", 7, truncation="fixed", max_bond=D)
+    f = net.forward(X)
+    fa = net.apply_act_func(f)
+    acc_ref = net.accuracy(X, y, f)
+    mae_ref = np.abs(np.eye(Lbl)[y].T - fa.elem).mean()
+    acc, mae = net.evaluate(X, y)
+    assert acc == acc_ref and abs(mae - mae_ref) < 1e-13
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y.astype(np.int32)).cuda()
+    assert net.evaluate(Xd, yd) == (acc, mae)                           # device-resident inputs
+    fo = O.apply_act(orc.forward(X), act, orc.T)
+    assert abs(mae - np.abs(np.eye(Lbl)[y] - fo).mean()) < TOL
+
+
+# ------------------------------------------------------------------------------------------- f1
+class _Opaque(torch.utils.data.Dataset):
+    """Hides .data / .label: forces Network.train onto the reference's host collation (NC:324-325)."""
+
+    def __init__(self, ds):
+        self._ds = ds
+
+    def __len__(self):
+        return len(self._ds)
+
+    def __getitem__(self, i):
+        return self._ds[i]
+
+
+def _loaders(gen, opaque):
+    from torch.utils.data import DataLoader, SubsetRandomSampler
+    np.random.seed(0)
+    torch.manual_seed(0)
+    data, label = gen.create_dataset(600, 6, 0.7)
+    tl, vl, _ = gen.prepare_dataset(data, label, 1, 0.2, train_batch_size=240, val_batch_size=40, test_batch_size=40)
+    if opaque:
+        mk = lambda l: DataLoader(_Opaque(l.dataset), l.batch_size, sampler=l.sampler, drop_last=l.drop_last,
+                                  collate_fn=l.collate_fn)
+        tl, vl = mk(tl), mk(vl)
+    return tl, vl
+
+
+def test_train_resident_path_equals_host_collation(tn):
+    """Same seeds -> same sampler draws -> bitwise the same training run whether the batches are gathered on the device
+    from the resident dataset or collated on the host from list[(x, y)]."""
+    import tensornetworkforml_b200.data_generator as gen
+    out = []
+    for opaque in (False, True):
+        tl, vl = _loaders(gen, opaque)
+        cal = next(iter(tl))
+        xcal = np.array([c[0] for c in cal])
+        with quiet():
+            net = tn.Network(N=36, M=6, L=2, calibration_X=xcal, normalize=True, act_fn="softmax", loss_fn="full_cross_ent")
+            assert (net._resident(tl) is None) == opaque
+            val_acc, var_hist = net.train(tl, vl, lr=0.01, n_epochs=3, weight_dec=1)
+        out.append((np.array(val_acc), var_hist, [np.asarray(T.elem).copy() for T in net.As]))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert all(np.array_equal(a, b) for a, b in zip(out[0][2], out[1][2]))
+    assert out[0][1].shape == (3, 2, 2 * 35)                            # two batches per epoch
+
+
+def test_train_at_config3_size_spends_its_time_in_forward_and_sweep():
+    """SURVEY 8(f1) done-criterion: three epochs of train() at Ns = 60 000, S = 196 (D = 16 here to keep the test short)
+    cost at most 10 % more wall time than the bare device loop over the same sweeps."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import tensornetworkforml_b200 as tn
+    import tensornetworkforml_b200.data_generator as gen
+    from torch.utils.data import DataLoader, SubsetRandomSampler
+    S, Lbl, D, Ns, NV = 196, 10, 16, 60000, 2000
+    np.random.seed(2)
+    torch.manual_seed(2)
+    data, labels = gen.create_multiclass_dataset(Ns + NV, 14, Lbl, 0.7)
+    ds = gen.NumpyDataset(gen.psi(data.reshape(Ns + NV, -1)), labels.astype(np.int64))
+    tl = DataLoader(ds, Ns, sampler=SubsetRandomSampler(np.arange(Ns)), drop_last=True, collate_fn=lambda b: b)
+    vl = DataLoader(ds, NV, sampler=SubsetRandomSampler(np.arange(Ns, Ns + NV)), drop_last=True, collate_fn=lambda b: b)
+    with quiet():
+        net = tn.Network(N=S, M=D, L=Lbl, normalize=True, calibration_X=ds.data[:512], act_fn="linear", loss_fn="MSE",
+                         truncation="fixed", max_bond=D)
+        net.train(tl, vl, lr=1e-4, n_epochs=1, weight_dec=1e-3)         # warm-up: upload, allocations, first-use costs
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        net.train(tl, vl, lr=1e-4, n_epochs=3, weight_dec=1e-3)
+        torch.cuda.synchronize()
+        t_train = time.perf_counter() - t0
+    eng = net._engine()
+    ydev = torch.from_numpy(labels[:Ns].astype(np.int32)).cuda()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.forward()
+        left = eng.l_pos == S - 1
+        eng.begin_sweep(ydev, left, True)
+        for _ in range(S - 1):
+            eng.sweep_step(1e-4, 1e-3, True, left)
+        eng.history()
+    torch.cuda.synchronize()
+    t_bare = time.perf_counter() - t0
+    assert t_train < 1.10 * t_bare + 0.05, "train %.3f s vs bare device loop %.3f s" % (t_train, t_bare)
+
+
+# ------------------------------------------------------------------------------------------- f3
+def test_stable_softmax_kernel_and_sweep(tn):
+    from tensornetworkforml_b200 import _lib as L
+    rng = np.random.default_rng(8)
+    Ns, Lbl, T = 257, 5, 0.1
+    y = rng.integers(0, Lbl, Ns)
+    y1h = np.eye(Lbl)[y]
+    phi = O.feature_map(rng.random((Ns, 2)))
+    for scale in (1.0, 400.0):                                           # 400 / T = 4000: exp overflows (NC:794 -> nan)
+        f = rng.standard_normal((Ns, Lbl)) * scale
+        outs = {}
+        for act in ("softmax", "softmax_stable"):
+            fd = torch.from_numpy(f).cuda()
+            q = torch.empty(Ns * Lbl * 4, dtype=torch.float64, device="cuda")
+            pp = torch.empty(Ns * 4, dtype=torch.float64, device="cuda")
+            met = torch.empty(4, dtype=torch.float64, device="cuda")
+            ws = torch.empty(L.lib().tnml_act_lossder_workspace_bytes(Ns) // 8 + 1, dtype=torch.float64, device="cuda")
+            p0 = torch.from_numpy(np.ascontiguousarray(phi[:, 0])).cuda()
+            p1 = torch.from_numpy(np.ascontiguousarray(phi[:, 1])).cuda()
+            L.call("tnml_act_lossder", fd.data_ptr(), torch.from_numpy(y.astype(np.int32)).cuda().data_ptr(), p0.data_ptr(),
+                   p1.data_ptr(), q.data_ptr(), pp.data_ptr(), met.data_ptr(), ws.data_ptr(), Ns, Lbl, L.ACT[act],
+                   L.LOSS["cross_entropy"], T, L.F64, torch.cuda.current_stream().cuda_stream)
+            outs[act] = (q.cpu().numpy().reshape(Ns, Lbl, 4), met.cpu().numpy())
+        fa = O.apply_act(f, "softmax_stable", T)
+        g = O.loss_derivative(fa, y1h, "softmax_stable", "cross_entropy", T)
+        want = g[:, :, None] * np.einsum("bs,bt->bst", phi[:, 0], phi[:, 1]).reshape(Ns, 1, 4)
+        assert np.isfinite(outs["softmax_stable"][0]).all()
+        assert G.rel(outs["softmax_stable"][0], want) < 1e-12
+        assert abs(outs["softmax_stable"][1][1] - np.abs(y1h - fa).sum()) < 1e-9
+        if scale == 1.0:
+            assert G.rel(outs["softmax"][0], want) < 1e-12              # same values where the reference is finite
+        else:
+            assert not np.isfinite(outs["softmax"][0]).all()             # the reference's overflow, preserved by default
+    # a sweep with the option switched on follows the oracle's restatement
+    S, D, Ns = 8, 5, 128
+    X, y, orc, net = _pair(tn, S, D, 3, Ns, "softmax", "full_cross_ent", 9, truncation="fixed", max_bond=D,
+                           stable_softmax=True)
+    fo, f = orc.forward(X), net.forward(X)
+    fo = orc.sweep(y, fo, 0.01, 0.01, True, False)
+    f = net.sweep(X, y, f, 0.01, 0.01, L2_flag=True, left_dir=False)
+    assert G.rel(f.elem.T, fo) < TOL
+    assert G.rel(net.apply_act_func(f).elem.T, O.apply_act(fo, "softmax_stable", orc.T)) < TOL
+
+
+@pytest.mark.parametrize("threshold,min_bond", [(0.9, 2), (0.999, 3)])
+def test_adaptive_truncation_follows_the_oracle(tn, threshold, min_bond):
+    """truncation='adaptive': m = max(min_bond, min(index, max_bond)), index = argmax(cumsum(S)/sum(S) > threshold)
+    (NC:890-891, old_files/TensorNetwork.py:1310-1326).  Bond dimensions become data dependent; f, singular values and
+    bonds follow the oracle's restatement for two sweeps."""
+    S, D, Lbl, Ns = 10, 8, 3, 200
+    X, y, orc, net = _pair(tn, S, D, Lbl, Ns, "linear", "MSE", 10, truncation="adaptive", max_bond=D,
+                           threshold=threshold, min_bond=min_bond)
+    for sw in range(2):
+        fo, f = orc.forward(X), net.forward(X)
+        assert G.rel(f.elem.T, fo) < TOL
+        left = orc.l_pos == S - 1
+        n0 = len(orc.hist)
+        fo = orc.sweep(y, fo, 0.02, 0.01, True, left)
+        f = net.sweep(X, y, f, 0.02, 0.01, L2_flag=True, left_dir=left)
+        assert net._eng.bond_dims() == orc.bond_dims(), "sweep %d" % sw
+        assert G.rel(f.elem.T, fo) < TOL
+        assert net.last_history["m"] == [r["m"] for r in orc.hist[n0:]]
+        for mine, ref in zip(net.last_history["svals"], [r["S"] for r in orc.hist[n0:]]):
+            assert np.abs(mine[:len(ref)] - ref).max() / ref.max() < TOL
+    assert len(set(net._eng.bond_dims())) > 2 and max(net._eng.bond_dims()) <= D
