@@ -23,7 +23,8 @@ from __future__ import annotations
 
 import numpy as np
 
-ACT_FNS = ("linear", "sigmoid", "softmax", "softmax_stable")   # NC:127; 'softmax_stable' = opt-in extension
+ACT_FNS = ("linear", "sigmoid", "softmax")            # NC:127
+EXT_ACT_FNS = ("softmax_stable",)                      # opt-in extension, not in the reference
 LOSS_FNS = ("MSE", "cross_entropy", "full_cross_ent")  # NC:132
 
 
@@ -274,7 +275,7 @@ class OracleMPS:
 
     def __init__(self, sites, L, T=0.1, act_fn="linear", loss_fn="cross_entropy",
                  rule="reference", max_bond=None, l_pos=0, threshold=0.999, min_bond=2):
-        assert act_fn in ACT_FNS and loss_fn in LOSS_FNS
+        assert act_fn in ACT_FNS + EXT_ACT_FNS and loss_fn in LOSS_FNS
         self.sites = [np.array(s, dtype=np.float64) for s in sites]
         self.S = len(sites)
         self.L = L

@@ -410,10 +410,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     }
     ++tphase;
   };
-  auto fail = [&]() {
-    if (tid == 0) { skip[2] = 0.0; skip[1] = 1.0; }
+  // a refused split leaves its reason in info[2] (1 no warm basis, 2 CholeskyQR breakdown, 3 residual after two
+  // subspace steps, 4 final gates) and the deciding ratio in info[3]
+  auto fail = [&](int code, double val) {
+    if (tid == 0) {
+      skip[2] = 0.0;
+      skip[1] = 1.0;
+      if (info) { info[2] = (double)code; info[3] = val; }
+    }
   };
-  if (!(hdr[0] == 1.0 && hdr[1] == (double)FS_N && hdr[2] == (double)FS_M)) { fail(); return; }   // uniform
+  if (!(hdr[0] == 1.0 && hdr[1] == (double)FS_N && hdr[2] == (double)FS_M)) { fail(1, hdr[0]); return; }   // uniform
   // V0 = rows 0 .. m-1 of the warm buffer
   for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) A1[(e >> 7) * FS_LDV + (e & 127)] = vt[e];
   // trace of G (warp 0)
@@ -425,9 +431,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   }
   __syncthreads();
   tick();                                              // 0: load
-  double resid2 = 0.0, trT = 0.0, mind = 0.0;
+  // Subspace steps: each one contracts the angle to the dominant subspace by lambda_{m+1} / lambda_m (1e-12 on the bench
+  // workload: one step; 1e-4 early in training or with a large learning rate: three).  A step that gains less than a
+  // factor 30 ends the attempt: the cold pipeline is cheaper than many more of them.
+  double resid2 = 0.0, trT = 0.0, mind = 0.0, resid2_prev = 1e300;
   bool ok = false;
-  for (int iter = 0; iter < 2; ++iter) {
+  for (int iter = 0; iter < 4; ++iter) {
     tphase = 1;
     fs_gemm_vg(A1, G, A2, warp, lane);                 // Y = V G
     __syncthreads();
@@ -435,7 +444,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     fs_gemm_abt(A2, A2, Sm, warp, lane);               // S = Y Y^T
     __syncthreads();
     tick();                                            // 2
-    if (!fs_orthonormalize(Sm, A2, A1, yrow, scol, dsave, tid)) { fail(); return; }   // Q = D^-1/2 L^-1 Y
+    if (!fs_orthonormalize(Sm, A2, A1, yrow, scol, dsave, tid)) { fail(2, (double)iter); return; }   // Q = D^-1/2 L^-1 Y
     __syncthreads();
     tick();                                            // 3
     tick();                                            // 4
@@ -471,8 +480,10 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     __syncthreads();
     tick();                                            // 7: residual
     if (ok) break;                                      // otherwise iterate once more from Q (A1)
+    if (iter > 0 && !(resid2 < 1e-3 * resid2_prev)) break;
+    resid2_prev = resid2;
   }
-  if (!ok) { fail(); return; }
+  if (!ok) { fail(3, mind > 0.0 ? sqrt(resid2) / mind : -1.0); return; }
   const int sweeps = fs_jacobi_rows(Sm, nrm2, rot_count, 30, 64.0 * 4.930380657631324e-32, tid);
   tphase = 8;
   tick();                                              // 8: Jacobi
@@ -495,7 +506,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   // gates: residual against the TRUE lambda_m; the subspace is the dominant one (every outside eigenvalue below
   // lambda_m); every kept singular value in the range a single Gram pass resolves (sigma >= 1e-3 sigma_max)
   ok = lamm > 0.0 && resid2 <= 1e-24 * lamm * lamm && tau <= 0.25 * lamm && lamm >= 1e-6 * lam1 && sweeps < 30;
-  if (!ok) { fail(); return; }
+  if (!ok) {
+    fail(4, !(resid2 <= 1e-24 * lamm * lamm) ? 1.0 : (!(tau <= 0.25 * lamm) ? 2.0 + tau / lamm : (!(lamm >= 1e-6 * lam1)
+            ? 3.0 : 4.0)));
+    return;
+  }
   // U = W^T Q (unit rows of Sm in rank order) -> rows 0 .. m-1 of the warm buffer
   fs_gemm_ab(Sm, ord, A1, warp, lane, [&](int i, int j, double v) { vt[(size_t)i * FS_N + j] = v * invn[ord[i]]; });
   const double tail_mean = fmax(tau, 0.0) / (double)(FS_N - FS_M);

@@ -145,7 +145,17 @@ class SweepEngine:
         # the second and later visits of a bond try the deflation path first (svd_fast.cuh), verified on the device
         self.warm_split = os.environ.get("TNML_FAST_SPLIT", "1") != "0"
         self._warm = {}
-        self.project_ctas_fast = int(os.environ.get("TNML_PROJECT_CTAS_FAST", "146"))   # one CTA of the fast split + spare
+        # per (bond, direction): visits to sit out before the deflation path is tried again.  history() sees which
+        # attempts the device-side gates refused (a refused attempt costs the attempt plus the single-CTA form of the
+        # cold pipeline, which is slower than the cluster form): a refused bond goes back to the cold cluster pipeline
+        # for the next two visits.
+        self._warm_wait = {}
+        # Beside the single-CTA fast split the projection leaves two SMs free when it is the longer of the two (large
+        # per-GPU batches: the split's small multi-CTA kernels then queue for those two SMs, which does not matter), and
+        # sixteen when the split is the critical path (small per-GPU batches, i.e. many GPUs)
+        self.project_ctas_fast = int(os.environ.get("TNML_PROJECT_CTAS_FAST", "146"))
+        self.project_ctas_fast_small = int(os.environ.get("TNML_PROJECT_CTAS_FAST_SMALL", "132"))
+        self.project_bound_flops = float(os.environ.get("TNML_PROJECT_BOUND_GFLOP", "10")) * 1e9
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -441,7 +451,7 @@ class SweepEngine:
                          metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
                          stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
-                         nsv=[], m=[], n=0)
+                         nsv=[], m=[], n=0, fast_keys=[], fast_seen=0)
         self.hist["tail_recs"][:, 1] = 1.0            # "nothing recorded" until a tail call writes the header
         self._st = None
 
@@ -602,8 +612,11 @@ class SweepEngine:
                 warm = self._warm[key] = torch.zeros(nw, dtype=torch.float64, device=self.device)
                 if side is not main:
                     side.wait_stream(main)              # the zero fill ran on the main stream
+            elif self._warm_wait.get(key, 0) > 0:
+                self._warm_wait[key] -= 1
             else:
                 fast = 1
+            self.hist["fast_keys"].append((step, key) if fast else None)
         with _Timed(self, "svd_split", 0.0, side):
             call("tnml_svd_split_warm", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), _ptr(warm), Dl, Dr, L,
                  m, ldir, 3 if defer else self.svd_refine, fast, F64, side.cuda_stream,
@@ -613,10 +626,13 @@ class SweepEngine:
             if split_done is None:
                 split_done = self._split_evt[par] = torch.cuda.Event()
             split_done.record(side)
-        if gram_done is not None:
+        # fast split: is the projection (8 Ns L Dl Dr flops at ~25 TFLOP/s) longer than the ~0.35 ms split?
+        project_bound = 8.0 * Ns * L * Dl * Dr > self.project_bound_flops
+        if gram_done is not None and not (fast and project_bound):
             # the split's SM-holding Cholesky cluster must be placed before the projection fills the GPU: the projection
             # becomes eligible a few microseconds after the event (without the pause the order was a race that the
-            # first process on a fresh box lost: 454 instead of 345 ms per sweep)
+            # first process on a fresh box lost: 454 instead of 345 ms per sweep).  With the fast split the event only
+            # lets the Gram kernels run unhindered; a projection that is the critical path does not wait for it.
             main.wait_event(gram_done)
             if not fast:
                 call("tnml_delay", self.project_delay_ns, st)
@@ -625,7 +641,7 @@ class SweepEngine:
             # single-CTA fast split two SMs
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
             if fast and cap:
-                cap = self.project_ctas_fast
+                cap = self.project_ctas_fast if project_bound else self.project_ctas_fast_small
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
                  Dl, Dr, L, cap, self.DT, st)
         if defer:
@@ -709,6 +725,11 @@ class SweepEngine:
         acc = met[:, 0] / total                                   # NC:700
         mae = met[:, 1] / (total * self.L)                        # NC:702
         svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
+        fk = self.hist["fast_keys"]
+        for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)
+            if ent is not None and not sv[ent[0], self.hist["nsv"][ent[0]]] >= 100:
+                self._warm_wait[ent[1]] = 2
+        self.hist["fast_seen"] = len(fk)
         return dict(acc=acc, mae=mae, stats=stats, svals=svals, m=list(self.hist["m"]))
 
     def bond_dims(self):

@@ -74,7 +74,9 @@ def test_three_interior_bond_updates_at_config3_shape(tn):
         prod = np.einsum("asm,mtlc->asltc", eng.sites[p].cpu().numpy().reshape(D, 2, -1),
                          eng.sites[p + 1].cpu().numpy().reshape(-1, 2, L, D))
         want = np.einsum("asm,mtlc->asltc", orc.sites[p], orc.sites[p + 1])
-        assert G.rel(prod, want) < TOL, "A_p' A_q', step %d" % step
+        # the left bond a of this pair carries the sign gauge of the previous split (u_k, v_k -> -u_k, -v_k): align it
+        sgn = np.sign(np.einsum("asltc,asltc->a", prod, want))
+        assert G.rel(prod * sgn[:, None, None, None, None], want) < TOL, "A_p' A_q', step %d" % step
     h = eng.history()
     for step in range(n):
         ref = orc.hist[step]
@@ -112,15 +114,18 @@ def test_fixed_bond_128_sweeps_match_oracle(tn):
 
 
 def test_warm_started_split_inside_sweeps(tn):
-    """Six sweeps of a chain with config-3 bond dimensions (D = 64, L = 10).  From the third sweep on the interior splits
-    start from the previous visit's basis (csrc/svd_fast.cuh).  (1) The run with the fast path equals the run without
-    it (cold pipeline every time) to 1e-10 in f and singular values, sweep by sweep; (2) both follow the oracle
+    """Six sweeps of a 16-site chain with config-3 bond dimensions (D = 64, L = 10) on the bench's stripe data.  From the third sweep on the interior splits
+    start from the previous visit's basis (csrc/svd_fast.cuh).  (1) Every sweep with the fast path equals the same sweep without
+    it (cold pipeline, restarted from the same tensors) to 1e-10 in f and singular values; (2) both follow the oracle
     (free-running: 1e-7 after six sweeps of a chaotic iteration -- a 1e-15 perturbation reaches 5e-8 after six
     reference sweeps); (3) the fast path was taken."""
-    S, D, Lbl, Ns, lr, wd = 14, 64, 10, 1024, 1e-3, 1e-3
-    np.random.seed(41)
-    X = O.feature_map(np.random.random((Ns, S)))
-    y = np.random.randint(0, Lbl, Ns)
+    import tensornetworkforml_b200.data_generator as gen
+    side, D, Lbl, Ns, lr, wd = 4, 64, 10, 2048, 1e-4, 1e-3          # the bench workload (stripe templates) in small
+    S = side * side
+    np.random.seed(2)
+    data, labels = gen.create_multiclass_dataset(Ns, side, Lbl, 0.7)
+    X, y = gen.psi(data.reshape(Ns, -1)), labels.astype(np.int64)
+    np.random.seed(2)
     state = np.random.get_state()
     orc = O.OracleMPS.from_seed(S, D, Lbl, calibration_X=X, normalize=True, act_fn="linear", loss_fn="MSE", rule="fixed",
                                 max_bond=D)
@@ -138,6 +143,11 @@ def test_warm_started_split_inside_sweeps(tn):
         left = orc.l_pos == S - 1
         n0 = len(orc.hist)
         fo = orc.sweep(y, fo, lr, wd, L2_flag=True, left_dir=left)
+        if sw > 0:      # the cold run restarts every sweep from the fast run's tensors: a per-sweep comparison from identical
+            import copy  # states (free-running, the two would drift apart like any two roundings of a chaotic iteration)
+            with quiet():
+                nets[1].As = copy.deepcopy(nets[0].As)
+                nets[1].l_pos = nets[0].l_pos
         outs = []
         for net in nets:
             f = net.forward(X)
