@@ -12,8 +12,9 @@ namespace tnml {
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
                                               const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
-                                              int ldc) {
+                                              int ldc, const double* __restrict__ skip_if) {
   __shared__ double As[16][65];
+  if (skip_if && *skip_if != 0.0) return;   // device-side switch (the warm-started split's optional second subspace step)
   __shared__ double Bs[16][65];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -68,13 +69,13 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha,
 }
 
 static int launch_gemm(int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
-                       int ldb, double beta, double* C, int ldc, cudaStream_t st) {
+                       int ldb, double beta, double* C, int ldc, cudaStream_t st, const double* skip_if = nullptr) {
   dim3 grid(tnml_cdiv(N, 64), tnml_cdiv(M, 64));
   TNML_COUNT(1);
-  if (!tA && !tB) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (tA && !tB) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-  else if (!tA && tB) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
-  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+  if (!tA && !tB) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else if (tA && !tB) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else if (!tA && tB) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
   return tnml_launch_status();
 }
 
@@ -152,6 +153,13 @@ __global__ void __launch_bounds__(BU_THREADS) k_bu_apply(const double* __restric
 }  // namespace tnml
 
 using namespace tnml;
+
+namespace tnml {
+int gemm_if(const double* skip_if, int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda,
+            const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st) {
+  return launch_gemm(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st, skip_if);
+}
+}  // namespace tnml
 
 extern "C" int tnml_gemm(int32_t transA, int32_t transB, int32_t M, int32_t N, int32_t K, double alpha, const void* A,
                          int32_t lda, const void* B, int32_t ldb, double beta, void* C, int32_t ldc, int32_t dtype,

@@ -121,6 +121,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                : "memory");
 }
 
+// C = alpha op(A) op(B) + beta C like tnml_gemm (bond.cu); returns at once on the device when *skip_if != 0.
+int gemm_if(const double* skip_if, int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda,
+            const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t st);
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

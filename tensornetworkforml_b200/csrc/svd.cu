@@ -545,8 +545,9 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
 // ---------------------------------------------------------------------------------------------------
 template <int NP>
 __global__ void __launch_bounds__(1024, 1) k_chol_big(double* __restrict__ Wg, int n, int cap_rows,
-                                                      int* __restrict__ flags_out) {
+                                                      int* __restrict__ flags_out, const double* __restrict__ fastf) {
   constexpr int NT = 1024, NG = NT / NP, NWG = NP / 32;
+  if (fastf && *fastf != 0.0) return;                    // the warm-started split delivered this pass
   extern __shared__ __align__(16) double cache[];        // cap_rows x NP: factor rows 0 .. cap_rows-1 in pivot order
   __shared__ double part[NG][NP], diag[NP];
   __shared__ unsigned char active[NP];
@@ -1027,6 +1028,7 @@ __global__ void __launch_bounds__(512) k_jacobi_cluster_w8(double* __restrict__ 
   constexpr int NP = 32 * E, NBmax = NP / K, KT = 32 * K;   // KT = threads of one block pair
   extern __shared__ __align__(16) double sm[];   // per block pair: 2K rows x NP, then 2K norms
   if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) return;   // uniform over the whole cluster
+  if (pass_id == 1 && skip_flag && skip_flag[2] != 0.0) return;  // the warm-started split delivered this pass
   int NB = NBmax;
   if (sub) {
     const int nact = sub[0];
@@ -1154,6 +1156,7 @@ __global__ void __launch_bounds__(512) k_jacobi_finish(const double* __restrict_
                                                        double* __restrict__ warm_hdr = nullptr, int m_keep = 0) {
   __shared__ double nrm[SVD_MAXN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
+  if (pass_id == 1 && skip_flag && skip_flag[2] != 0.0) return;   // the warm-started split delivered this pass
   if (pass_id >= 2 && skip_flag && *skip_flag != 0.0) {
     if (pass_id == 3) return;                        // deferred tail refinement not needed: leave everything alone
     // (the factor kernels read the skip flag themselves and fall back to the first pass's rotation and eigenvalues)
@@ -1496,8 +1499,9 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
     // on the small block keeps the plain Gram form
     if (use_chol && pass_id == 1 && chol_big_enabled()) {
       TNML_COUNT(1);
-      if (NP == 256) k_chol_big<256><<<1, 1024, CHOL_BIG_CAP_256 * 256 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_256, jb.flags);
-      else k_chol_big<512><<<1, 1024, CHOL_BIG_CAP_512 * 512 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_512, jb.flags);
+      const double* ff = skip ? skip + 2 : nullptr;
+      if (NP == 256) k_chol_big<256><<<1, 1024, CHOL_BIG_CAP_256 * 256 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_256, jb.flags, ff);
+      else k_chol_big<512><<<1, 1024, CHOL_BIG_CAP_512 * 512 * 8, st>>>(jb.Wg, n, CHOL_BIG_CAP_512, jb.flags, ff);
     } else {
       use_chol = 0;
     }
@@ -1606,7 +1610,8 @@ __global__ void __launch_bounds__(256) k_short(const double* __restrict__ Vt1, c
 struct SvdPlan {
   int R, C, n, Nl, nparts, lc, NP;
   bool rows_short;
-  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, off_Wg, off_nrm, off_flags, off_sub, total;
+  size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, off_Wg, off_nrm, off_flags, off_sub, off_fg,
+      total;
 };
 
 static SvdPlan svd_plan_rc(int R, int C) {
@@ -1634,12 +1639,260 @@ static SvdPlan svd_plan_rc(int R, int C) {
   p.off_nrm = o; o += p.NP;
   p.off_flags = o; o += 32;   // 64 ints
   p.off_sub = o; o += 2;      // 4 ints: {ns, k0} of the second pass, the two-group split flag, spare
+  // warm-started split for n = 256 / 512 (generic form: GEMMs in global memory, see fast_generic): G, six (n/2) x n
+  // panels, three (n/2) x (n/2) matrices, eigenvalues, gate scalars, the inner solve's own flags
+  p.off_fg = o;
+  if (p.n > 128) o += (size_t)p.n * p.n + 6 * (size_t)(p.n / 2) * p.n + 3 * (size_t)(p.n / 2) * (p.n / 2) + p.n + 32;
   p.total = o;
   return p;
 }
 
 static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
   return svd_plan_rc(left_dir ? 2 * Dl * L : 2 * Dl, left_dir ? 2 * Dr : 2 * L * Dr);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warm-started split, generic form for n = 256 / 512 (bond dimension 128 / 256, m = n / 2): the same algorithm as
+// k_fast_split (svd_fast.cuh) with the panels in global memory (L2) and every step a kernel of its own --
+//   Y = V0 G  ->  rows scaled to unit length, Newton-Schulz Y <- (3/2) Y - (1/2) (Y Y^T) Y  (GEMM-only orthonormalisation:
+//   the warm basis makes Y Y^T = I + O(1e-2), four steps reach rounding)  ->  Z = Q G, T = Q Z^T, R = Z - T Q
+//   ->  T = W diag(lam) W^T by the ordinary pipeline at HALF the size (launch_jacobi on the m x m matrix: an eighth of the
+//   Jacobi work)  ->  U = W^T Q  ->  gates, commit.
+// All steps run unconditionally (a refused attempt wastes them; the host backs off for the next visits of that bond),
+// only k_fg_commit decides: on success it publishes U, lam and the flags that make the cold pipeline behind it return at
+// once; otherwise it leaves skip[2] = 0 and the cold pipeline runs.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FastGenericWs {
+  double *G, *P[6], *M3[3], *lamT, *gate, *skipin;
+};
+static FastGenericWs fast_generic_ws(double* w, const SvdPlan& p) {
+  FastGenericWs f;
+  const size_t n = p.n, m = p.n / 2;
+  double* o = w + p.off_fg;
+  f.G = o; o += n * n;
+  for (int i = 0; i < 6; ++i) { f.P[i] = o; o += m * n; }
+  for (int i = 0; i < 3; ++i) { f.M3[i] = o; o += m * m; }
+  f.lamT = o; o += n;
+  f.gate = o; o += 16;
+  f.skipin = o; o += 16;
+  return f;
+}
+
+// rows of Y (m x n) scaled to unit length; one warp per row
+__global__ void __launch_bounds__(256) k_fg_row_scale(double* __restrict__ Y, int m, int n,
+                                                      const double* __restrict__ skip_if) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= m || (skip_if && *skip_if != 0.0)) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) { const double v = Y[(size_t)r * n + j]; s = fma(v, v, s); }
+  s = warp_sum(s);
+  const double inv = s > 0.0 ? 1.0 / sqrt(s) : 0.0;
+  for (int j = lane; j < n; j += 32) Y[(size_t)r * n + j] *= inv;
+}
+
+// T <- (T + T^T) / 2 in place (m x m)
+__global__ void __launch_bounds__(256) k_fg_copy(double* __restrict__ dst, const double* __restrict__ src, size_t count,
+                                                 const double* __restrict__ skip_if) {
+  if (skip_if && *skip_if != 0.0) return;
+  for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < count; e += (size_t)gridDim.x * 256) dst[e] = src[e];
+}
+
+__global__ void __launch_bounds__(256) k_fg_symmetrize(double* __restrict__ T, int m, const double* __restrict__ skip_if) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= m * m || (skip_if && *skip_if != 0.0)) return;
+  const int i = e / m, j = e % m;
+  if (i < j) {
+    const double v = 0.5 * (T[(size_t)i * m + j] + T[(size_t)j * m + i]);
+    T[(size_t)i * m + j] = v;
+    T[(size_t)j * m + i] = v;
+  }
+}
+
+// gate[0] = |R|_F^2, gate[1] = trace(G), gate[2] = trace(T), gate[3] = max |Q Q^T - I|, gate[4] = warm header valid;
+// also clears the inner solve's flags.  One CTA.
+__global__ void __launch_bounds__(1024) k_fg_gate(const double* __restrict__ R, const double* __restrict__ G,
+                                                  const double* __restrict__ T, const double* __restrict__ QQt,
+                                                  const double* __restrict__ hdr, int n, int m, double* __restrict__ gate,
+                                                  double* __restrict__ skipin, const double* __restrict__ skip_if) {
+  __shared__ double red[32], redm[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (skip_if && *skip_if != 0.0) return;
+  double s = 0.0, mx = 0.0;
+  for (size_t e = tid; e < (size_t)m * n; e += 1024) { const double v = R[e]; s = fma(v, v, s); }
+  for (int e = tid; e < m * m; e += 1024) {
+    const double v = QQt[e] - ((e / m == e % m) ? 1.0 : 0.0);
+    mx = fmax(mx, fabs(v));
+  }
+  s = warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) { red[warp] = s; redm[warp] = mx; }
+  __syncthreads();
+  if (warp == 0) {
+    s = red[lane];
+    mx = redm[lane];
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double tg = 0.0, tt = 0.0, md = 1e300;
+    for (int i = lane; i < n; i += 32) tg += G[(size_t)i * n + i];
+    for (int i = lane; i < m; i += 32) { const double d = T[(size_t)i * m + i]; tt += d; md = fmin(md, d); }
+    tg = warp_sum(tg);
+    tt = warp_sum(tt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) md = fmin(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if (lane == 0) {
+      gate[0] = s; gate[1] = tg; gate[2] = tt; gate[3] = mx;
+      // gate[5] != 0: this subspace step already reached the residual bound (against the smallest diagonal entry of T, an
+      // upper bound of lambda_m): the optional second step returns at once
+      gate[5] = (md > 0.0 && mx <= 1e-13 && s <= 0.25e-24 * md * md) ? 1.0 : 0.0;
+      gate[4] = (hdr[0] == 1.0 && hdr[1] == (double)n && hdr[2] == (double)m) ? 1.0 : 0.0;
+      skipin[0] = skipin[1] = skipin[2] = skipin[3] = 0.0;
+    }
+  }
+}
+
+// The decision.  lamT: eigenvalues of T (descending); U: m x n; on success rows 0..m-1 of vt <- U, lam, flags.
+__global__ void __launch_bounds__(1024) k_fg_commit(const double* __restrict__ U, const double* __restrict__ lamT,
+                                                    const double* __restrict__ gate, const double* __restrict__ info_in,
+                                                    int n, int m, double* __restrict__ vt, double* __restrict__ lam,
+                                                    double* __restrict__ skip, int* __restrict__ sub,
+                                                    double* __restrict__ info) {
+  const double lam1 = lamT[0], lamm = lamT[m - 1];
+  const double resid2 = gate[0], tau = gate[1] - gate[2];
+  int code = 0;
+  if (gate[4] == 0.0) code = 1;
+  else if (!(gate[3] <= 1e-13)) code = 2;                          // Newton-Schulz did not reach an orthonormal basis
+  else if (!(lamm > 0.0 && resid2 <= 1e-24 * lamm * lamm)) code = 3;
+  else if (!(tau <= 0.25 * lamm && lamm >= 1e-6 * lam1 && info_in[0] < 40.0)) code = 4;
+  if (code) {                                                       // uniform: every thread read the same values
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+      skip[2] = 0.0;
+      skip[1] = 1.0;
+      if (info) { info[2] = (double)code; info[3] = code == 3 ? (lamm > 0.0 ? sqrt(resid2) / lamm : -1.0) : gate[3]; }
+    }
+    return;
+  }
+  for (size_t e = (size_t)blockIdx.x * 1024 + threadIdx.x; e < (size_t)m * n; e += (size_t)gridDim.x * 1024) vt[e] = U[e];
+  if (blockIdx.x == 0) {
+    const double tail_mean = fmax(tau, 0.0) / (double)(n - m);
+    for (int i = threadIdx.x; i < n; i += 1024) lam[i] = i < m ? lamT[i] : tail_mean;
+    if (threadIdx.x == 0) {
+      skip[0] = 1.0; skip[1] = 0.0; skip[2] = 1.0;
+      sub[0] = n - m; sub[1] = m;
+      if (info) info[0] = 100.0 + info_in[0];
+    }
+  }
+}
+
+// Orthonormalise the rows of the m x n panel A (ping-pong with B) by `iters` Newton-Schulz steps; S: m x m scratch.
+// Returns the panel that holds the result.
+static double* fg_newton_schulz(double* A, double* B, double* S, int m, int n, int iters, cudaStream_t st, int* rc,
+                                const double* skip_if = nullptr) {
+  TNML_COUNT(1 + iters);
+  k_fg_row_scale<<<tnml_cdiv(m, 8), 256, 0, st>>>(A, m, n, skip_if);
+  for (int it = 0; it < iters && *rc == 0; ++it) {
+    *rc = gemm_if(skip_if, 0, 1, m, m, n, 1.0, A, n, A, n, 0.0, S, m, st);
+    if (*rc) break;
+    k_fg_copy<<<64, 256, 0, st>>>(B, A, (size_t)m * n, skip_if);
+    *rc = gemm_if(skip_if, 0, 0, m, n, m, -0.5, S, m, A, n, 1.5, B, n, st);
+    double* t = A; A = B; B = t;
+  }
+  return A;
+}
+
+// One Rayleigh-Ritz evaluation of the orthonormal basis Q: Z = Q G, T = Q Z^T (symmetrised), R = Z - T Q, gates.
+static int fg_rayleigh_ritz(const double* Q, const double* Gs, double* Z, double* T, double* R, double* S, const double* hdr,
+                            int n, int m, double* gate, double* skipin, cudaStream_t st, const double* skip_if) {
+  int rc = gemm_if(skip_if, 0, 1, m, m, n, 1.0, Q, n, Q, n, 0.0, S, m, st);                  // Q Q^T (orthonormality gate)
+  if (rc) return rc;
+  rc = gemm_if(skip_if, 0, 0, m, n, n, 1.0, Q, n, Gs, n, 0.0, Z, n, st);                     // Z = Q G
+  if (rc) return rc;
+  rc = gemm_if(skip_if, 0, 1, m, m, n, 1.0, Q, n, Z, n, 0.0, T, m, st);                      // T = Q Z^T
+  if (rc) return rc;
+  TNML_COUNT(3);
+  k_fg_symmetrize<<<tnml_cdiv(m * m, 256), 256, 0, st>>>(T, m, skip_if);
+  k_fg_copy<<<64, 256, 0, st>>>(R, Z, (size_t)m * n, skip_if);
+  rc = gemm_if(skip_if, 0, 0, m, n, m, -1.0, T, m, Q, n, 1.0, R, n, st);                     // R = Z - T Q
+  if (rc) return rc;
+  k_fg_gate<<<1, 1024, 0, st>>>(R, Gs, T, S, hdr, n, m, gate, skipin, skip_if);
+  return tnml_launch_status();
+}
+
+static int fast_generic(const double* Gs, const SvdPlan& p, int m, double* vt1, double* lam1, double* skip, int* sub,
+                        double* info, double* w, JacobiBuffers jb, cudaStream_t st) {
+  const int n = p.n;
+  FastGenericWs f = fast_generic_ws(w, p);
+  double *Ya = f.P[0], *Yb = f.P[1], *Z = f.P[2], *R = f.P[3], *U = f.P[4];
+  double *S = f.M3[0], *T = f.M3[1], *VtT = f.M3[2];
+  int rc = tnml_gemm(0, 0, m, n, n, 1.0, vt1, n, Gs, n, 0.0, Ya, n, TNML_F64, st);          // Y = V0 G
+  if (rc) return rc;
+  double* Q = fg_newton_schulz(Ya, Yb, S, m, n, 4, st, &rc);                                 // (four steps: back in Ya)
+  if (rc) return rc;
+  rc = fg_rayleigh_ritz(Q, Gs, Z, T, R, S, vt1 + (size_t)n * n, n, m, f.gate, f.skipin, st, nullptr);
+  if (rc) return rc;
+  // Second subspace step from Y = Z (= Q G), into the same buffers; every kernel of it returns at once when the first
+  // step already met the residual bound (gate[5]), which is the case whenever the basis is warm and the gap at m is
+  // wide (lambda_{m+1} / lambda_m ~ 1e-12 on the bench workload).
+  const double* done1 = f.gate + 5;
+  TNML_COUNT(1);
+  k_fg_copy<<<64, 256, 0, st>>>(Ya, Z, (size_t)m * n, done1);
+  Q = fg_newton_schulz(Ya, Yb, S, m, n, 4, st, &rc, done1);
+  if (rc) return rc;
+  rc = fg_rayleigh_ritz(Q, Gs, Z, T, R, S, vt1 + (size_t)n * n, n, m, f.gate, f.skipin, st, done1);
+  if (rc) return rc;
+  // eigen-decomposition of T by the ordinary first pass at size m (its own flags; rows of VtT = eigenvectors, sorted)
+  const double tol_m = sqrt((double)m) * 2.220446049250313e-16;
+  rc = launch_jacobi(T, 1, m, VtT, f.lamT, tol_m, 1, 1, f.gate + 8, f.skipin, nullptr, jb, nullptr, st, 0, 0, nullptr,
+                     nullptr, nullptr, false, nullptr);
+  if (rc) return rc;
+  rc = tnml_gemm(0, 0, m, n, m, 1.0, VtT, m, Q, n, 0.0, U, n, TNML_F64, st);                 // U = W^T Q
+  if (rc) return rc;
+  k_fg_commit<<<8, 1024, 0, st>>>(U, f.lamT, f.gate, f.gate + 8, n, m, vt1, lam1, skip, sub, info);
+  return tnml_launch_status();
+}
+
+// Off the critical path after a generic fast split: rows m..n-1 of the warm buffer <- orth(P0 - (P0 Q^T) Q).
+__global__ void __launch_bounds__(1024) k_fg_commit_complement(const double* __restrict__ P, const double* __restrict__ PPt,
+                                                               int n, int m, double* __restrict__ vt,
+                                                               double* __restrict__ skip) {
+  __shared__ int bad;
+  if (skip[2] == 0.0) return;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const int k = n - m;
+  for (int e = threadIdx.x; e < k * k; e += 1024) {
+    const double v = PPt[e] - ((e / k == e % k) ? 1.0 : 0.0);
+    if (!(fabs(v) <= 1e-13)) bad = 1;
+  }
+  __syncthreads();
+  if (bad) {
+    if (threadIdx.x == 0) skip[1] = 1.0;            // no complement basis: the tail values stay unrefined
+    return;
+  }
+  for (size_t e = threadIdx.x; e < (size_t)k * n; e += 1024) vt[(size_t)m * n + e] = P[e];
+}
+
+static int fast_generic_complement(const SvdPlan& p, int m, double* vt1, double* skip, double* w, cudaStream_t st) {
+  const int n = p.n, k = p.n - m;
+  FastGenericWs f = fast_generic_ws(w, p);
+  double *Pa = f.P[0], *Pb = f.P[1], *C = f.M3[0];
+  const double *Q = vt1, *P0 = vt1 + (size_t)m * n;
+  int rc = tnml_copy(Pa, P0, (int64_t)k * n * 8, st);
+  for (int pass = 0; pass < 2 && rc == 0; ++pass) {                                          // P <- P - (P Q^T) Q, twice
+    rc = tnml_gemm(0, 1, k, m, n, 1.0, Pa, n, Q, n, 0.0, C, m, TNML_F64, st);
+    if (rc) break;
+    rc = tnml_gemm(0, 0, k, n, m, -1.0, C, m, Q, n, 1.0, Pa, n, TNML_F64, st);
+  }
+  if (rc) return rc;
+  double* P = fg_newton_schulz(Pa, Pb, C, k, n, 4, st, &rc);
+  if (rc) return rc;
+  rc = tnml_gemm(0, 1, k, k, n, 1.0, P, n, P, n, 0.0, C, k, TNML_F64, st);
+  if (rc) return rc;
+  TNML_COUNT(1);
+  k_fg_commit_complement<<<1, 1024, 0, st>>>(P, C, n, m, vt1, skip);
+  return tnml_launch_status();
 }
 
 static int fast_split_enabled() {   // TNML_FAST_SPLIT=0: never take the warm-started fast path (A/B knob)
@@ -1651,6 +1904,9 @@ static int fast_split_enabled() {   // TNML_FAST_SPLIT=0: never take the warm-st
   return v;
 }
 static bool fast_split_shape(int n, int m) { return n == FS_N && m == FS_M && fast_split_enabled(); }
+static bool fast_generic_shape(int n, int m) {
+  return (n == 256 || n == 512) && 2 * m == n && fast_split_enabled() && jacobi_variant() == 2 && chol_big_enabled();
+}
 
 // Shared implementation: X = R x C row-major matrix, rowmap/colmap = where row i / column j of the factors land.
 static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_rows, Idx3 rowmap, long long row_k,
@@ -1682,6 +1938,7 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   // fast mode: the warm-started deflation split first; the single-CTA pipeline behind it only runs when a gate failed
   // (a cluster launch could not even be SCHEDULED to return early while the projection occupies the GPU)
   const bool fast = fast_hint && warm && refine == 3 && fast_split_shape(n, m);
+  const bool fastg = fast_hint && warm && refine == 3 && fast_generic_shape(n, m);   // n = 256 / 512: generic form
   const bool cluster = !fast && (n > 128 || (n > 64 && jacobi_cluster_enabled()));
   const int m_defer = (refine == 3 && cluster) ? m : 0;     // refine 3 = refine 1 + deferred tail (svd_tail)
   if (refine == 3) refine = 1;
@@ -1702,6 +1959,15 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
                                                  nullptr, nullptr, nullptr, m, nullptr, 0LL, 0, skip + 2, warm_hdr);
     rc = tnml_launch_status();
   } else {
+    if (fastg) {
+      TNML_COUNT(1);
+      double* Gs = fast_generic_ws(w, p).G;
+      k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, p.nparts, n, n, Gs, jb.flags, nullptr, 1, nullptr, 1);
+      rc = fast_generic(Gs, p, m, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n, w, jb, st);
+      if (rc) return rc;
+    } else if (skip1) {
+      cudaMemsetAsync(skip + 2, 0, sizeof(double), st);   // no fast attempt: the cold kernels must not see a stale flag
+    }
     rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer,
                        m, (int*)(w + p.off_sub) + 2, gram_done, warm_hdr);
     if (rc == 0 && warm_hdr && !cluster) {            // single-CTA pipeline (n <= 64): the header is written separately
@@ -1922,6 +2188,10 @@ extern "C" int tnml_svd_split_tail_warm(const void* Bnew, void* svals, void* ws,
   const SvdPlan p = svd_plan(Dl, Dr, L, left_dir);
   const bool fastm = fast && warm && record && fast_split_shape(p.n, m);
   const bool cluster = fastm || p.n > 128 || (p.n > 64 && jacobi_cluster_enabled());
+  if (fast && warm && fast_generic_shape(p.n, m)) {   // refresh the complement basis the tail pass projects on
+    const int rc = fast_generic_complement(p, m, (double*)warm, (double*)ws + p.off_skip, (double*)ws, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   if (record && cluster && p.n <= 128 && p.n - m <= 64)      // the deferred block has at most n - m <= 64 rows
     return svd_tail_record((const double*)Bnew, p, m, (double*)record, (double*)ws, (cudaStream_t)stream, (double*)warm,
                            fastm);

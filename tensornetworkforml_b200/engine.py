@@ -604,7 +604,8 @@ class SweepEngine:
             gram_done = self._gram_evt
         # warm buffer of this (bond, direction); `fast` = the bond was split before in this direction with these shapes
         warm, fast = None, 0
-        if defer and self.warm_split and min(R, Cc) == 128 and m == 64:
+        nshort = min(R, Cc)
+        if defer and self.warm_split and nshort in (128, 256, 512) and 2 * m == nshort:
             key = (p, ldir, Dl, Dr)
             warm = self._warm.get(key)
             if warm is None:
@@ -628,19 +629,20 @@ class SweepEngine:
             split_done.record(side)
         # fast split: is the projection (8 Ns L Dl Dr flops at ~25 TFLOP/s) longer than the ~0.35 ms split?
         project_bound = 8.0 * Ns * L * Dl * Dr > self.project_bound_flops
-        if gram_done is not None and not (fast and project_bound):
+        fast128 = bool(fast and nshort == 128)        # single-CTA form; the generic form (n = 256 / 512) still uses clusters
+        if gram_done is not None and not (fast128 and project_bound):
             # the split's SM-holding Cholesky cluster must be placed before the projection fills the GPU: the projection
             # becomes eligible a few microseconds after the event (without the pause the order was a race that the
             # first process on a fresh box lost: 454 instead of 345 ms per sweep).  With the fast split the event only
             # lets the Gram kernels run unhindered; a projection that is the critical path does not wait for it.
             main.wait_event(gram_done)
-            if not fast:
+            if not fast128:
                 call("tnml_delay", self.project_delay_ns, st)
         with _Timed(self, "project", 8.0 * Ns * L * Dl * Dr):
             # beside a cluster-parallel SVD the projection leaves the 8 SMs of the split's cluster free; beside the
             # single-CTA fast split two SMs
             cap = self.project_ctas if (side is not main and min(R, Cc) > 64) else 0
-            if fast and cap:
+            if fast128 and cap:
                 cap = self.project_ctas_fast if project_bound else self.project_ctas_fast_small
             call("tnml_project", _ptr(Bn), _ptr(self.pp_buf), self._env(p), self._env(q + 1), _ptr(f_out), _ptr(ws), Ns,
                  Dl, Dr, L, cap, self.DT, st)

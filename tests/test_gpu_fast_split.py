@@ -54,6 +54,7 @@ class Splitter:
                self.ws.data_ptr(), self.warm.data_ptr(), Dl, Dr, nl, m, left_dir, 3, fast, L.F64, st(), None)
         torch.cuda.synchronize()
         marker = float(sv[n].item())                    # 100 + sweeps when the fast path delivered the split
+        self.refusal = (float(sv[n + 2].item()), float(sv[n + 3].item()))
         L.call("tnml_svd_split_tail_warm", Bd.data_ptr(), sv.data_ptr(), self.ws.data_ptr(), rec.data_ptr(),
                self.warm.data_ptr(), Dl, Dr, nl, m, left_dir, fast, L.F64, st())
         L.call("tnml_svd_tail_batch", rec.data_ptr(), 1, sv.data_ptr(), sv.numel(), L.F64, st())
@@ -80,15 +81,18 @@ def check(Mx, sv, prod, m, US):
     assert np.abs(G - np.diag(S[:m])).max() / S.max() < 1e-10
 
 
+SIZES = [(64, 10), (128, 3), (256, 2)]     # (bond dimension, labels): short side 128 (single-CTA form), 256, 512 (generic)
+
+
 @pytest.mark.parametrize("left_dir", [0, 1])
 @pytest.mark.parametrize("spread", [0.5, 0.997])
-def test_fast_path_is_taken_and_matches_svd(L, left_dir, spread):
+@pytest.mark.parametrize("D,nl", SIZES)
+def test_fast_path_is_taken_and_matches_svd(L, left_dir, spread, D, nl):
     """Visit 1 (cold) fills the warm buffer; visits 2.. of a slowly drifting matrix take the deflation path (marker) and
     agree with np.linalg.svd, including the discarded tail after the deferred refinement.  spread = 0.997 is the
     interior of the bench chain: all kept singular values within 0.3 % of each other."""
     rng = np.random.default_rng(20 + left_dir)
-    Dl = Dr = 64
-    nl, m = 10, 64
+    Dl = Dr = m = D
     sp = Splitter(L, Dl, Dr, nl, left_dir, m)
     Mx = bond_like(rng, Dl, Dr, nl, left_dir, spread)
     sv, prod, marker, US = sp.run(Mx, fast=0)
@@ -98,17 +102,17 @@ def test_fast_path_is_taken_and_matches_svd(L, left_dir, spread):
         # drift: a rank-n/2 change of relative size 1e-3 (rotates the dominant subspace) plus full-rank noise at 1e-6
         Mx = Mx + 1e-3 * bond_like(rng, Dl, Dr, nl, left_dir, spread) + 1e-6 * np.abs(Mx).max() * rng.standard_normal(Mx.shape)
         sv, prod, marker, US = sp.run(Mx, fast=1)
-        assert marker >= 100, "visit %d fell back to the cold pipeline" % visit
+        assert marker >= 100, "visit %d fell back to the cold pipeline %r" % (visit, sp.refusal)
         check(Mx, sv, prod, m, US)
 
 
 @pytest.mark.parametrize("left_dir", [0, 1])
-def test_gates_fall_back_to_the_cold_pipeline(L, left_dir):
+@pytest.mark.parametrize("D,nl", SIZES[:2])
+def test_gates_fall_back_to_the_cold_pipeline(L, left_dir, D, nl):
     """fast = 1 on inputs the deflation path must refuse: an unvisited warm buffer, no gap at m, a stale basis of an
     unrelated matrix (accepted only if the device-side gates pass; the result must be right either way)."""
     rng = np.random.default_rng(30 + left_dir)
-    Dl = Dr = 64
-    nl, m = 10, 64
+    Dl = Dr = m = D
     sp = Splitter(L, Dl, Dr, nl, left_dir, m)
     Mx = bond_like(rng, Dl, Dr, nl, left_dir)
     sv, prod, marker, US = sp.run(Mx, fast=1)             # header invalid: nothing to start from
@@ -128,10 +132,10 @@ def test_gates_fall_back_to_the_cold_pipeline(L, left_dir):
     check(Ms, sv, prod, m, US)
 
 
-def test_fast_split_is_deterministic(L):
+@pytest.mark.parametrize("D,nl", SIZES[:2])
+def test_fast_split_is_deterministic(L, D, nl):
     rng = np.random.default_rng(40)
-    Dl = Dr = 64
-    nl, m = 10, 64
+    Dl = Dr = m = D
     Mx = bond_like(rng, Dl, Dr, nl, 0)
     Mx2 = Mx + 1e-5 * rng.standard_normal(Mx.shape)
     outs = []
