@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ns", type=int, default=CFG["Ns"], help="total samples (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the API arm (bond-dimension sweeps: device numbers only)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="f64 = the parity path (default, the BASELINE metric); f32 = FP32 storage / TF32 tcgen05 variant")
     ap.add_argument("--D", type=int, default=CFG["D"], help="bond dimension (other BASELINE.json configs)")
@@ -305,6 +306,9 @@ def main():
         jacobi_sweeps = dict(pass1_mean=float(np.nanmean(p1)), pass1_max=float(np.nanmax(p1)),
                              pass2_mean=float(np.nanmean(jac[:, 1])), pass2_max=float(np.nanmax(jac[:, 1])),
                              warm_started_fraction=float(fast.mean()),
+                             refusals={("code%d" % int(c)): int(n) for c, n in zip(*np.unique(
+                                 [sv_raw[i, nsv[i] + 2] for i in range(len(nsv)) if nsv[i] == 2 * D and
+                                  not sv_raw[i, nsv[i]] >= 100 and np.isfinite(sv_raw[i, nsv[i] + 2])], return_counts=True))},
                              note="last sweep, splits with short side 2D; warm-started = svd_fast.cuh path taken")
     smin = np.array([hist["svals"][i][-1] / hist["svals"][i][0] for i in range(len(nsv)) if nsv[i] == 2 * D])
     spectrum = dict(sigma_min_over_max_median=float(np.median(smin)), sigma_min_over_max_min=float(smin.min())) if len(smin) else None
@@ -356,27 +360,30 @@ def main():
                                              "gaps, against the same FP64 DMMA peak (x n_gpus)")
 
     # ---- end-to-end arm through the reference-facing API (host buffers) -------------------------------
-    net.l_pos, net._host_fresh = eng.l_pos, False       # the device arm drove the engine directly
-    net.register_input(X)                               # the caller's batch, page-locked in place (explicit opt-in)
-    for _ in range(max(1, min(args.warmup, 2))):
-        api_step()
-    barrier()
-    api_t.update(forward=0.0, sweep=0.0, n=0)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        f_host = api_step()
-    e1.record()
-    barrier()
-    wall = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    e2e = dict(value=n_updates / (e2e_ms * 1e-3), unit="bond-updates/s", h2d_bytes_per_step=int(X.nbytes + y.size * 4),
-               d2h_bytes_per_step=int(f_host.elem.nbytes + (S - 1) * (4 + 6 + 4 * D) * 8),
-               ms_per_step=e2e_ms / args.steps, api="Network.forward(X_host) + Network.sweep(X_host, y_host, f)",
-               forward_ms=api_t["forward"] / max(1, api_t["n"]) * 1e3, sweep_ms=api_t["sweep"] / max(1, api_t["n"]) * 1e3)
+    e2e = None
+    if not args.no_e2e:
+        net.l_pos, net._host_fresh = eng.l_pos, False       # the device arm drove the engine directly
+        net.register_input(X)                               # the caller's batch, page-locked in place (explicit opt-in)
+        for _ in range(max(1, min(args.warmup, 2))):
+            api_step()
+        barrier()
+        api_t.update(forward=0.0, sweep=0.0, n=0)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            f_host = api_step()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(e0.elapsed_time(e1), wall)], dtype=torch.float64, device=eng.device)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+        e2e = dict(value=n_updates / (e2e_ms * 1e-3), unit="bond-updates/s", h2d_bytes_per_step=int(X.nbytes + y.size * 4),
+                   d2h_bytes_per_step=int(f_host.elem.nbytes + (S - 1) * (4 + 6 + 4 * D) * 8),
+                   ms_per_step=e2e_ms / args.steps, api="Network.forward(X_host) + Network.sweep(X_host, y_host, f)",
+                   forward_ms=api_t["forward"] / max(1, api_t["n"]) * 1e3,
+                   sweep_ms=api_t["sweep"] / max(1, api_t["n"]) * 1e3)
 
     line = dict(metric="bond_updates_per_s", value=value, unit="bond-updates/s", n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms / args.steps, s_per_sweep=ms / args.steps * 1e-3,

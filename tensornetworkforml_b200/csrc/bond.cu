@@ -5,61 +5,77 @@
 namespace tnml {
 
 // ---------------------------------------------------------------------------------------------------
-// Row-major C = alpha * op(A) . op(B) + beta * C.  64x64 tile, 256 threads, 4x4 register tile (plain DFMA:
-// these products are at most tens of MFLOP and never leave L2).
+// Row-major C = alpha * op(A) . op(B) + beta * C.  T x T tile (T = 64: 4x4 register tile, T = 32: 2x2), 256 threads,
+// plain DFMA (on B200 the DFMA and DMMA peaks coincide; these products are at most a few hundred MFLOP and never
+// leave L2).  The next k-slice is fetched into registers while the current one is multiplied: the kernels are short
+// chains of k-slices on few CTAs, i.e. bound by the L2 latency of each slice, not by throughput.  T = 32 is chosen for
+// small outputs (four times the CTAs: the warm-started split's 128 x 256 panels run on 32 instead of 8 SMs).
 // TA: A stored K x M (element (m,k) at k*lda + m).  TB: B stored N x K (element (k,n) at n*ldb + k).
+// skip_if (device, optional): the kernel returns at once when *skip_if != 0.
 // ---------------------------------------------------------------------------------------------------
-template <bool TA, bool TB>
+template <bool TA, bool TB, int T>
 __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
                                               const double* __restrict__ B, int ldb, double beta, double* __restrict__ C,
                                               int ldc, const double* __restrict__ skip_if) {
-  __shared__ double As[16][65];
-  if (skip_if && *skip_if != 0.0) return;   // device-side switch (the warm-started split's optional second subspace step)
-  __shared__ double Bs[16][65];
+  constexpr int R = T / 16;            // register tile R x R
+  constexpr int PT = T * 16 / 256;     // elements of each operand slice per thread (4 or 2)
+  __shared__ double As[16][T + 1];
+  __shared__ double Bs[16][T + 1];
+  if (skip_if && *skip_if != 0.0) return;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  double acc[4][4];
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  double acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+  double pa[PT], pb[PT];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < PT; ++i) {
+      const int e = tid + 256 * i;
+      int m, k;
+      if (TA) { m = e % T; k = e / T; } else { k = e & 15; m = e >> 4; }
+      pa[i] = (m0 + m < M && k0 + k < K) ? (TA ? A[(size_t)(k0 + k) * lda + m0 + m] : A[(size_t)(m0 + m) * lda + k0 + k]) : 0.0;
+      int n, kk;
+      if (TB) { kk = e & 15; n = e >> 4; } else { n = e % T; kk = e / T; }
+      pb[i] = (n0 + n < N && k0 + kk < K) ? (TB ? B[(size_t)(n0 + n) * ldb + k0 + kk] : B[(size_t)(k0 + kk) * ldb + n0 + n]) : 0.0;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < K; k0 += 16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + 256 * i;
+    for (int i = 0; i < PT; ++i) {
+      const int e = tid + 256 * i;
       int m, k;
-      if (TA) { m = e & 63; k = e >> 6; } else { k = e & 15; m = e >> 4; }
-      double v = 0.0;
-      if (m0 + m < M && k0 + k < K) v = TA ? A[(size_t)(k0 + k) * lda + m0 + m] : A[(size_t)(m0 + m) * lda + k0 + k];
-      As[k][m] = v;
+      if (TA) { m = e % T; k = e / T; } else { k = e & 15; m = e >> 4; }
+      As[k][m] = pa[i];
       int n, kk;
-      if (TB) { kk = e & 15; n = e >> 4; } else { n = e & 63; kk = e >> 6; }
-      double w = 0.0;
-      if (n0 + n < N && k0 + kk < K) w = TB ? B[(size_t)(n0 + n) * ldb + k0 + kk] : B[(size_t)(k0 + kk) * ldb + n0 + n];
-      Bs[kk][n] = w;
+      if (TB) { kk = e & 15; n = e >> 4; } else { n = e % T; kk = e / T; }
+      Bs[kk][n] = pb[i];
     }
     __syncthreads();
+    if (k0 + 16 < K) fetch(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      double a[4], b[4];
+      double a[R], b[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+      for (int i = 0; i < R; ++i) a[i] = As[k][ty + 16 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+      for (int j = 0; j < R; ++j) b[j] = Bs[k][tx + 16 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < R; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < R; ++i) {
     int m = m0 + ty + 16 * i;
     if (m >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < R; ++j) {
       int n = n0 + tx + 16 * j;
       if (n >= N) continue;
       double* c = C + (size_t)m * ldc + n;
@@ -68,14 +84,24 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, double alpha,
   }
 }
 
+template <int T>
+static void launch_gemm_t(int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
+                          int ldb, double beta, double* C, int ldc, cudaStream_t st, const double* skip_if) {
+  dim3 grid(tnml_cdiv(N, T), tnml_cdiv(M, T));
+  if (!tA && !tB) k_gemm<false, false, T><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else if (tA && !tB) k_gemm<true, false, T><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else if (!tA && tB) k_gemm<false, true, T><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  else k_gemm<true, true, T><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+}
+
 static int launch_gemm(int tA, int tB, int M, int N, int K, double alpha, const double* A, int lda, const double* B,
                        int ldb, double beta, double* C, int ldc, cudaStream_t st, const double* skip_if = nullptr) {
-  dim3 grid(tnml_cdiv(N, 64), tnml_cdiv(M, 64));
   TNML_COUNT(1);
-  if (!tA && !tB) k_gemm<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
-  else if (tA && !tB) k_gemm<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
-  else if (!tA && tB) k_gemm<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
-  else k_gemm<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, skip_if);
+  // fewer than one 64 x 64 tile per SM: 32 x 32 tiles spread the product over four times as many SMs
+  if ((int64_t)tnml_cdiv(M, 64) * tnml_cdiv(N, 64) < tnml_num_sms())
+    launch_gemm_t<32>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st, skip_if);
+  else
+    launch_gemm_t<64>(tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, st, skip_if);
   return tnml_launch_status();
 }
 

@@ -1656,7 +1656,7 @@ static SvdPlan svd_plan(int Dl, int Dr, int L, int left_dir) {
 // Warm-started split, generic form for n = 256 / 512 (bond dimension 128 / 256, m = n / 2): the same algorithm as
 // k_fast_split (svd_fast.cuh) with the panels in global memory (L2) and every step a kernel of its own --
 //   Y = V0 G  ->  rows scaled to unit length, Newton-Schulz Y <- (3/2) Y - (1/2) (Y Y^T) Y  (GEMM-only orthonormalisation:
-//   the warm basis makes Y Y^T = I + O(1e-2), four steps reach rounding)  ->  Z = Q G, T = Q Z^T, R = Z - T Q
+//   the warm basis makes Y Y^T = I + O(1e-2), six steps reach rounding from 0.3)  ->  Z = Q G, T = Q Z^T, R = Z - T Q
 //   ->  T = W diag(lam) W^T by the ordinary pipeline at HALF the size (launch_jacobi on the m x m matrix: an eighth of the
 //   Jacobi work)  ->  U = W^T Q  ->  gates, commit.
 // All steps run unconditionally (a refused attempt wastes them; the host backs off for the next visits of that bond),
@@ -1821,14 +1821,17 @@ static int fg_rayleigh_ritz(const double* Q, const double* Gs, double* Z, double
 }
 
 static int fast_generic(const double* Gs, const SvdPlan& p, int m, double* vt1, double* lam1, double* skip, int* sub,
-                        double* info, double* w, JacobiBuffers jb, cudaStream_t st) {
+                        double* info, double* w, JacobiBuffers jb, cudaStream_t st, cudaEvent_t cluster_placed) {
   const int n = p.n;
   FastGenericWs f = fast_generic_ws(w, p);
   double *Ya = f.P[0], *Yb = f.P[1], *Z = f.P[2], *R = f.P[3], *U = f.P[4];
   double *S = f.M3[0], *T = f.M3[1], *VtT = f.M3[2];
   int rc = tnml_gemm(0, 0, m, n, n, 1.0, vt1, n, Gs, n, 0.0, Ya, n, TNML_F64, st);          // Y = V0 G
   if (rc) return rc;
-  double* Q = fg_newton_schulz(Ya, Yb, S, m, n, 4, st, &rc);                                 // (four steps: back in Ya)
+  // six steps (an even count: the result is back in Ya): |Y Y^T - I| = 0.3 -> 7e-2 -> 3e-3 -> 9e-6 -> 6e-11 -> rounding;
+  // four were not enough at the chain ends, where the kept singular values spread over a factor 2-3 and the rows of Y
+  // overlap by a few 1e-2 (12 of 52 attempts refused at bond dimension 128)
+  double* Q = fg_newton_schulz(Ya, Yb, S, m, n, 6, st, &rc);
   if (rc) return rc;
   rc = fg_rayleigh_ritz(Q, Gs, Z, T, R, S, vt1 + (size_t)n * n, n, m, f.gate, f.skipin, st, nullptr);
   if (rc) return rc;
@@ -1838,14 +1841,17 @@ static int fast_generic(const double* Gs, const SvdPlan& p, int m, double* vt1, 
   const double* done1 = f.gate + 5;
   TNML_COUNT(1);
   k_fg_copy<<<64, 256, 0, st>>>(Ya, Z, (size_t)m * n, done1);
-  Q = fg_newton_schulz(Ya, Yb, S, m, n, 4, st, &rc, done1);
+  Q = fg_newton_schulz(Ya, Yb, S, m, n, 6, st, &rc, done1);
   if (rc) return rc;
   rc = fg_rayleigh_ritz(Q, Gs, Z, T, R, S, vt1 + (size_t)n * n, n, m, f.gate, f.skipin, st, done1);
   if (rc) return rc;
   // eigen-decomposition of T by the ordinary first pass at size m (its own flags; rows of VtT = eigenvectors, sorted)
   const double tol_m = sqrt((double)m) * 2.220446049250313e-16;
+  // (m = 128: the inner pipeline records `cluster_placed` right before its SM-holding Cholesky cluster, so that a caller
+  // running the projection on another stream can let it start only then -- a cluster of 8 CTAs needs 8 free SMs in one
+  // GPC, which it does not find once the projection occupies the GPU: the split then waited for the projection to drain)
   rc = launch_jacobi(T, 1, m, VtT, f.lamT, tol_m, 1, 1, f.gate + 8, f.skipin, nullptr, jb, nullptr, st, 0, 0, nullptr,
-                     nullptr, nullptr, false, nullptr);
+                     cluster_placed, nullptr, false, nullptr);
   if (rc) return rc;
   rc = tnml_gemm(0, 0, m, n, m, 1.0, VtT, m, Q, n, 0.0, U, n, TNML_F64, st);                 // U = W^T Q
   if (rc) return rc;
@@ -1963,7 +1969,7 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
       TNML_COUNT(1);
       double* Gs = fast_generic_ws(w, p).G;
       k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, p.nparts, n, n, Gs, jb.flags, nullptr, 1, nullptr, 1);
-      rc = fast_generic(Gs, p, m, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n, w, jb, st);
+      rc = fast_generic(Gs, p, m, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n, w, jb, st, gram_done);
       if (rc) return rc;
     } else if (skip1) {
       cudaMemsetAsync(skip + 2, 0, sizeof(double), st);   // no fast attempt: the cold kernels must not see a stale flag

@@ -9,7 +9,8 @@ from tensornetworkforml_b200 import _lib as L
 from test_gpu_fast_split import bond_like
 
 L.lib()
-Dl = Dr = 64; nl, m = 10, 64
+Dl = Dr = m = int(os.environ.get("D", 64)); nl = int(os.environ.get("NL", 10))
+NSV = 2 * Dl
 for left_dir in (0, 1):
     for spread in (0.5, 0.997):
         rng = np.random.default_rng(1)
@@ -18,7 +19,7 @@ for left_dir in (0, 1):
         warm = torch.zeros(lib.tnml_svd_warm_bytes(Dl, Dr, nl, left_dir) // 8, dtype=torch.float64, device="cuda")
         site_p = torch.empty(Dl * 2 * m * nl, dtype=torch.float64, device="cuda")
         site_q = torch.empty(m * 2 * Dr * nl, dtype=torch.float64, device="cuda")
-        sv = torch.zeros(512, dtype=torch.float64, device="cuda")
+        sv = torch.zeros(4096, dtype=torch.float64, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
         Mx = bond_like(rng, Dl, Dr, nl, left_dir, spread)
         for visit in range(4):
@@ -39,5 +40,5 @@ for left_dir in (0, 1):
                     warm.copy_(wsave)
             s = sv.cpu().numpy()
             print("left_dir=%d spread=%.3f visit %d fast=%d: %s us, marker %d, phase cycles %s" % (
-                left_dir, spread, visit, fast, ["%.0f" % t for t in ts], int(s[128]), [int(x) for x in s[132:142]]), flush=True)
+                left_dir, spread, visit, fast, ["%.0f" % t for t in ts], int(s[NSV]), [int(x) for x in s[NSV + 4:NSV + 14]]), flush=True)
             Mx = Mx + 1e-3 * bond_like(rng, Dl, Dr, nl, left_dir, spread)

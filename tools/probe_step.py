@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import tensornetworkforml_b200 as tn
 
-S, D, L, Ns = int(os.environ.get("PS", 20)), 64, 10, int(os.environ.get("PNS", 8192))
+S, D, L, Ns = int(os.environ.get("PS", 20)), int(os.environ.get("PD", 64)), 10, int(os.environ.get("PNS", 8192))
 np.random.seed(0)
 X = np.random.random((Ns, S)); X = np.stack((np.sin(np.pi * X / 2), np.cos(np.pi * X / 2)), -1)
 y = np.random.randint(0, L, Ns)
