@@ -150,6 +150,7 @@ class SweepEngine:
         # cold pipeline, which is slower than the cluster form): a refused bond goes back to the cold cluster pipeline
         # for the next two visits.
         self._warm_wait = {}
+        self._warm_fail = {}
         # Beside the single-CTA fast split the projection leaves two SMs free when it is the longer of the two (large
         # per-GPU batches: the split's small multi-CTA kernels then queue for those two SMs, which does not matter), and
         # sixteen when the split is the critical path (small per-GPU batches, i.e. many GPUs)
@@ -237,6 +238,7 @@ class SweepEngine:
         self.l_pos = int(l_pos)
         self.label_layout = "R"
         self._warm = {}               # new weights: the rotations of earlier visits say nothing about them
+        self._warm_wait, self._warm_fail = {}, {}
         for p, A in enumerate(host_sites):
             A = np.ascontiguousarray(A, dtype=np.float64)
             if p == self.l_pos:
@@ -729,8 +731,19 @@ class SweepEngine:
         svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
         fk = self.hist["fast_keys"]
         for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)
-            if ent is not None and not sv[ent[0], self.hist["nsv"][ent[0]]] >= 100:
-                self._warm_wait[ent[1]] = 2
+            if ent is None:
+                continue
+            nsv_i = self.hist["nsv"][ent[0]]
+            if sv[ent[0], nsv_i] >= 100:
+                self._warm_fail.pop(ent[1], None)
+                continue
+            # refused.  Code 3 = the subspace had not converged after the allowed steps: typical for the first sweeps of a
+            # training run, when the tensors still change a lot between visits -- try again at the next visit.  Anything
+            # else (no gap at m, ill-conditioned basis), or a second refusal in a row: sit out two visits.
+            fails = self._warm_fail.get(ent[1], 0) + 1
+            self._warm_fail[ent[1]] = fails
+            code = sv[ent[0], nsv_i + 2]
+            self._warm_wait[ent[1]] = 0 if (code == 3.0 and fails < 2) else 2
         self.hist["fast_seen"] = len(fk)
         return dict(acc=acc, mae=mae, stats=stats, svals=svals, m=list(self.hist["m"]))
 
