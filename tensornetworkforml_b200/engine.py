@@ -737,13 +737,13 @@ class SweepEngine:
             if sv[ent[0], nsv_i] >= 100:
                 self._warm_fail.pop(ent[1], None)
                 continue
-            # refused.  Code 3 = the subspace had not converged after the allowed steps: typical for the first sweeps of a
-            # training run, when the tensors still change a lot between visits -- try again at the next visit.  Anything
-            # else (no gap at m, ill-conditioned basis), or a second refusal in a row: sit out two visits.
+            # refused.  In the first sweeps of a training run the tensors still change a lot between visits (the basis
+            # of the previous visit is then a poor start: the subspace steps do not converge, or the orthonormalisation
+            # does not): try again at the next visit.  A second refusal in a row (no gap at m -- typical for the bonds
+            # next to the chain ends): sit out two visits, then try again.
             fails = self._warm_fail.get(ent[1], 0) + 1
             self._warm_fail[ent[1]] = fails
-            code = sv[ent[0], nsv_i + 2]
-            self._warm_wait[ent[1]] = 0 if (code == 3.0 and fails < 2) else 2
+            self._warm_wait[ent[1]] = 0 if fails < 2 else 2
         self.hist["fast_seen"] = len(fk)
         return dict(acc=acc, mae=mae, stats=stats, svals=svals, m=list(self.hist["m"]))
 
