@@ -75,6 +75,13 @@ int tnml_host_unregister(void* host_ptr);
  * tnml_feature_map   : phi[s][b][:] = [sin(pi x[b][s]/2), cos(pi x[b][s]/2)]  (sin first)   DG:165-167, NC:152-155
  * tnml_pack_features : X[b][s][:] (the (Ns,S,2) array the reference API takes) -> phi[s][b][:]   NC:222-225 */
 int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream);
+/* Synthetic images generated on the device (the caller side of DG:6-52): labels[b] from a counter-based generator
+ * (prob_first >= 0: two labels, label 0 with that probability like np.random.choice at DG:42; prob_first < 0: uniform
+ * over n_labels), x[b][s] = templates[labels[b]][s] * (1 - sigma) + uniform[0,1) * sigma (DG:49-50).  templates is a
+ * device array [n_labels][S].  Deterministic in (seed, Ns, S); NOT NumPy's stream -- seeded reference scripts keep using
+ * the host generator of data_generator.py. */
+int tnml_generate_dataset(const void* templates, void* x, int32_t* labels, int64_t Ns, int32_t S, int32_t n_labels,
+                          double sigma, double prob_first, uint64_t seed, tnml_stream_t stream);
 int tnml_pack_features(const void* X, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream);
 
 /* ---- a5/a10: environment advance ------------------------------------------------------------------

@@ -194,6 +194,18 @@ class Network():
         self._last_f = None
         return eng.eval_metrics()
 
+    def forward_raw(self, x):
+        """forward() for RAW pixels x of shape (batch, N) or (batch, d, d) -- host array or CUDA tensor (e.g. from
+        data_generator.create_dataset_device): the feature map psi (DG:165-167) runs on the device."""
+        eng = self._engine()
+        xr = x.reshape(x.shape[0], -1)
+        assert self.N == xr.shape[1], "The 1 dimension of the input data must be the flattened number of pixels"
+        eng.load_raw(xr)
+        f_dev = eng.forward()
+        out = Tensor(elem=f_dev.t().cpu().numpy().astype(np.float64), axes_names=['l', 'b'])
+        self._last_f = out
+        return out
+
     # ------------------------------------------------------------------ train (NC:261-350)
     def _resident(self, loader):
         """(data, labels) of the loader's dataset on the device, uploaded ONCE, when the dataset is array-backed

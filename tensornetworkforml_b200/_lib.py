@@ -25,6 +25,7 @@ SIGNATURES = {
     "tnml_host_register": (C.c_int, [_vp, C.c_uint64]),
     "tnml_host_unregister": (C.c_int, [_vp]),
     "tnml_feature_map": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
+    "tnml_generate_dataset": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f64, _f64, C.c_uint64, _vp]),
     "tnml_pack_features": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "tnml_env_advance": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "tnml_site_transpose": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),

@@ -294,7 +294,46 @@ __global__ void __launch_bounds__(256) k_site_predict(const double* __restrict__
 
 }  // namespace tnml
 
+namespace tnml {
+// Synthetic images on the device (DG:42-50): label[b] drawn from a counter-based generator (splitmix64 of (seed, b)),
+// x[b][s] = template[label[b]][s] * (1 - sigma) + u[b][s] * sigma with u uniform in [0, 1).  One thread per pixel.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long z) { return (double)(z >> 11) * (1.0 / 9007199254740992.0); }
+
+__global__ void __launch_bounds__(256) k_generate_dataset(const double* __restrict__ templates, double* __restrict__ x,
+                                                          int* __restrict__ labels, long long Ns, int S, int n_labels,
+                                                          double sigma, double prob_first, unsigned long long seed) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= Ns * S) return;
+  const long long b = e / S;
+  const int s = (int)(e % S);
+  const double ul = u01(splitmix64(seed * 0xD1342543DE82EF95ull + 2 * (unsigned long long)b + 1));
+  int lab;
+  if (prob_first >= 0.0) lab = ul < prob_first ? 0 : 1;                  // np.random.choice([0, 1], p=[p, 1-p])  DG:42
+  else lab = min(n_labels - 1, (int)(ul * n_labels));
+  if (s == 0) labels[b] = lab;
+  const double un = u01(splitmix64((seed ^ 0xA5A5A5A5A5A5A5A5ull) * 0x9E3779B97F4A7C15ull + 2 * (unsigned long long)e));
+  x[e] = templates[(long long)lab * S + s] * (1.0 - sigma) + un * sigma;   // DG:49-50
+}
+}  // namespace tnml
+
 using namespace tnml;
+
+extern "C" int tnml_generate_dataset(const void* templates, void* x, int32_t* labels, int64_t Ns, int32_t S,
+                                     int32_t n_labels, double sigma, double prob_first, uint64_t seed,
+                                     tnml_stream_t stream) {
+  TNML_REQUIRE(templates && x && labels && Ns > 0 && S > 0 && n_labels > 0);
+  TNML_REQUIRE(prob_first < 0.0 || n_labels == 2);
+  TNML_COUNT(1);
+  k_generate_dataset<<<tnml_cdiv(Ns * S, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const double*)templates, (double*)x, (int*)labels, Ns, S, n_labels, sigma, prob_first, (unsigned long long)seed);
+  return tnml_launch_status();
+}
 
 extern "C" int tnml_feature_map(const void* x, void* phi, int64_t Ns, int32_t S, int32_t dtype, tnml_stream_t stream) {
   TNML_REQUIRE(dtype == TNML_F64 || dtype == TNML_F32);

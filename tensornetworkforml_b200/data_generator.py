@@ -22,9 +22,8 @@ def create_dataset(n_samples, linear_dim=5, sigma=0.5, prob_zero=0.5):
     return data * (1 - sigma) + noise, labels
 
 
-def create_multiclass_dataset(n_samples, linear_dim=14, n_labels=10, sigma=0.7):
-    """Additive extension (SURVEY.md section 8d, config 3): ``n_labels`` fixed stripe templates (even labels: row
-    stripes, odd labels: column stripes), ``label ~ randint``, mixed with uniform noise exactly like DG:49-50."""
+def stripe_templates(linear_dim=14, n_labels=10):
+    """The ``n_labels`` fixed stripe images of create_multiclass_dataset (even labels: row stripes, odd: column)."""
     templates = np.zeros((n_labels, linear_dim, linear_dim))
     period = max(2, (n_labels + 1) // 2)
     idx = np.arange(linear_dim)
@@ -34,9 +33,48 @@ def create_multiclass_dataset(n_samples, linear_dim=14, n_labels=10, sigma=0.7):
             templates[k] = stripe[:, None] * np.ones((1, linear_dim))
         else:
             templates[k] = np.ones((linear_dim, 1)) * stripe[None, :]
+    return templates
+
+
+def create_multiclass_dataset(n_samples, linear_dim=14, n_labels=10, sigma=0.7):
+    """Additive extension (SURVEY.md section 8d, config 3): ``n_labels`` fixed stripe templates (even labels: row
+    stripes, odd labels: column stripes), ``label ~ randint``, mixed with uniform noise exactly like DG:49-50."""
+    templates = stripe_templates(linear_dim, n_labels)
     labels = np.random.randint(0, n_labels, n_samples)
     noise = np.random.rand(n_samples, linear_dim, linear_dim) * sigma
     return templates[labels] * (1 - sigma) + noise, labels
+
+
+def _generate_on_device(templates, n_samples, sigma, prob_first, seed, device):
+    import torch
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise RuntimeError("the device-side generators need a CUDA device (there is no CPU fallback)")
+    dev = torch.device(device if device is not None else "cuda")
+    n_labels, side = templates.shape[0], templates.shape[1]
+    t = torch.from_numpy(np.ascontiguousarray(templates.reshape(n_labels, -1), dtype=np.float64)).to(dev)
+    x = torch.empty((n_samples, side, side), dtype=torch.float64, device=dev)
+    labels = torch.empty(n_samples, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("tnml_generate_dataset", t.data_ptr(), x.data_ptr(), labels.data_ptr(), n_samples, side * side,
+                  n_labels, float(sigma), float(prob_first), int(seed) & (2 ** 64 - 1),
+                  torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.current_stream(dev).synchronize()       # `t` is released when this function returns
+    return x, labels
+
+
+def create_dataset_device(n_samples, linear_dim=5, sigma=0.5, prob_zero=0.5, seed=0, device=None):
+    """create_dataset (DG:6-52) generated ON the device: (x (n, d, d) float64, labels (n,) int32) as CUDA tensors, ready
+    for ``Network.forward_raw`` -- nothing crosses PCIe.  Same construction (templates, label probabilities, noise
+    mixing); the random numbers come from a counter-based generator, not NumPy's stream, so use the host function when
+    a seeded reference run has to be reproduced."""
+    one = np.eye(linear_dim)
+    return _generate_on_device(np.stack([one[::-1, :], one]), n_samples, sigma, prob_zero, seed, device)
+
+
+def create_multiclass_dataset_device(n_samples, linear_dim=14, n_labels=10, sigma=0.7, seed=0, device=None):
+    """create_multiclass_dataset generated on the device (see create_dataset_device)."""
+    return _generate_on_device(stripe_templates(linear_dim, n_labels), n_samples, sigma, -1.0, seed, device)
 
 
 def get_MNIST_dataset(data_root_dir='./datasets', download=True):

@@ -334,7 +334,7 @@ class SweepEngine:
 
     def load_raw(self, x):
         """x: (Ns, S) raw pixels; the feature map phi = [sin, cos](pi x / 2) runs on the device (DG:165-167)."""
-        xd = x if (isinstance(x, torch.Tensor) and x.is_cuda) else torch.from_numpy(
+        xd = x.to(torch.float64) if (isinstance(x, torch.Tensor) and x.is_cuda) else torch.from_numpy(
             np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
         Ns = xd.shape[0]
         self._ald_for = None

@@ -264,3 +264,37 @@ def test_adaptive_truncation_follows_the_oracle(tn, threshold, min_bond):
     assert min_bond <= min(net._eng.bond_dims()[1:-1]) and max(net._eng.bond_dims()) <= D
     if threshold > 0.99:
         assert len(set(net._eng.bond_dims())) > 2                       # data-dependent bonds, not one constant
+
+
+# ------------------------------------------------------------------------------------------- f4
+def test_device_side_generators(tn):
+    """create_dataset / create_multiclass_dataset on the device (DG:6-52): same templates, label probabilities and noise
+    mixing as the host functions (checked through their statistics), deterministic in the seed, and the raw pixels feed
+    forward_raw (feature map on the device) with the same result as psi() + forward()."""
+    import tensornetworkforml_b200.data_generator as gen
+    n, d, sigma = 20000, 6, 0.7
+    x, lab = gen.create_dataset_device(n, d, sigma, prob_zero=0.3, seed=5)
+    x2, lab2 = gen.create_dataset_device(n, d, sigma, prob_zero=0.3, seed=5)
+    x3, _ = gen.create_dataset_device(n, d, sigma, prob_zero=0.3, seed=6)
+    assert torch.equal(x, x2) and torch.equal(lab, lab2) and not torch.equal(x, x3)
+    xh, lh = x.cpu().numpy(), lab.cpu().numpy()
+    assert abs((lh == 0).mean() - 0.3) < 0.02
+    one = np.eye(d)
+    tmpl = np.where((lh == 0)[:, None, None], one[::-1, :][None], one[None])
+    noise = (xh - tmpl * (1 - sigma)) / sigma                          # DG:49-50 inverted
+    assert noise.min() >= 0.0 and noise.max() < 1.0 and abs(noise.mean() - 0.5) < 5e-3 and abs(noise.var() - 1 / 12) < 5e-3
+    assert abs(np.corrcoef(noise[:, 0, 0], noise[:, 0, 1])[0, 1]) < 0.03
+    xm, lm = gen.create_multiclass_dataset_device(n, 14, 10, 0.7, seed=1)
+    lmh = lm.cpu().numpy()
+    assert np.abs(np.bincount(lmh, minlength=10) / n - 0.1).max() < 0.015
+    t = gen.stripe_templates(14, 10)
+    nz = (xm.cpu().numpy() - t[lmh] * 0.3) / 0.7
+    assert nz.min() >= 0.0 and nz.max() < 1.0 and abs(nz.mean() - 0.5) < 5e-3
+    # raw pixels -> feature map on the device == psi on the host
+    np.random.seed(3)
+    with quiet():
+        net = tn.Network(N=d * d, M=4, L=2, normalize=True, calibration_X=gen.psi(xh[:64].reshape(64, -1)),
+                         act_fn="linear", loss_fn="MSE")
+    f_dev = net.forward_raw(x[:500])
+    f_host = net.forward(gen.psi(xh[:500].reshape(500, -1)))
+    assert G.rel(f_dev.elem, f_host.elem) < 1e-13
