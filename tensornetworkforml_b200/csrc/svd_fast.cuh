@@ -30,11 +30,11 @@ constexpr int FS_OFF_A2 = FS_OFF_A1 + FS_M * FS_LDV;
 constexpr int FS_OFF_S = FS_OFF_A2 + FS_M * FS_LDV;
 constexpr int FS_OFF_W = FS_OFF_S + FS_M * FS_LDS;
 constexpr int FS_OFF_MISC = FS_OFF_W + FS_M * FS_LDS;
-constexpr int FS_MISC = 768;
+constexpr int FS_MISC = 1664;
 constexpr int FS_SMEM_BYTES = (FS_OFF_MISC + FS_MISC) * 8;
 // misc region (doubles): [0,64) pivots | [64,128) row norms | [128,384) pivot row of Y, double-buffered | [384,416) red |
 //                        [416,480) lam | [480,544) 1/norm | [544,576) ord (ints) | [576,580) scalars |
-//                        [592,720) pivot column of S, double-buffered
+//                        [832,1600) multipliers of the current elimination block
 constexpr int FS_HDR = 8;          // doubles behind the n x n warm matrix: {valid, n, m, ...}
 
 __device__ __forceinline__ double fs_rsqrt(double x) {   // x > 0, normal: MUFU seed + one third-order correction
@@ -151,67 +151,83 @@ __device__ __forceinline__ double fs_rcp(double x) {   // x > 0, normal: MUFU se
 }
 
 // CholeskyQR without the square roots on the critical path: S = Y Y^T = L D L^T (unit lower L) is eliminated and the
-// SAME elimination steps are applied to the rows of Y.  Both live in REGISTERS: thread = (column pair c, c + 64; rows
-// 4 j + g) of Y and (row si, columns sq + 4 u <= si) of the lower triangle of S; per step only the pivot column of S and
-// the pivot row of Y travel through (double-buffered) shared memory, so a step is ONE barrier and the chain
-// load pivot -> reciprocal -> multiplier -> FMA -> publish.  Out = D^-1/2 L^-1 Y has orthonormal rows.
+// SAME elimination steps are applied to the rows of Y, so that Out = D^-1/2 L^-1 Y has orthonormal rows.  BLOCKED, 8
+// columns at a time: inside a block eight short steps touch only the 64 x 8 panel of S and the block's eight rows of Y
+// (a few FMAs per thread, one barrier each: the chain load pivot -> reciprocal -> multiplier -> FMA is what bounds a
+// step), then ONE rank-8 trailing update of S and of the remaining rows of Y on the DMMA pipe.  72 barriers, 61 k cycles;
+// the un-blocked register-resident form before it took 64 steps of ~1300 cycles (in-order issue of ~190 instructions
+// per warp while the other warps waited at the barrier: 85 k), a right-looking Cholesky + forward substitution 164 k.
 // Returns false (uniformly) when a pivot falls below 1e-10 of the largest diagonal entry (Y was far from orthogonal: no
 // orthonormal basis to working accuracy).
-__device__ __forceinline__ bool fs_orthonormalize(const double* __restrict__ S, const double* __restrict__ Yin,
-                                                  double* __restrict__ Out, double* __restrict__ yrow,
-                                                  double* __restrict__ col, double* __restrict__ dsave, int tid) {
-  const int c = tid & 63, g = tid >> 6;                                   // Y: columns c, c + 64; rows 4 j + g
-  const int si = tid >> 2, sq = tid & 3;                                  // S: row si, columns sq + 4 u
-  double y[16][2], sreg[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) { y[j][0] = Yin[(4 * j + g) * FS_LDV + c]; y[j][1] = Yin[(4 * j + g) * FS_LDV + c + 64]; }
-#pragma unroll
-  for (int u = 0; u < 16; ++u) sreg[u] = (sq + 4 * u <= si) ? S[si * FS_LDS + sq + 4 * u] : 0.0;
+// S (stride FS_LDS) and Y (stride FS_LDV) are eliminated in place in shared memory; Out = D^-1/2 L^-1 Y.
+// Lp: 64 x FS_LDP multipliers of the current block.
+constexpr int FS_LDP = 12;
+__device__ __forceinline__ bool fs_orthonormalize_blocked(double* __restrict__ S, double* __restrict__ Y,
+                                                          double* __restrict__ Out, double* __restrict__ Lp,
+                                                          double* __restrict__ dsave, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, c4 = lane & 3;
   double dmax = 0.0;
   for (int k = 0; k < FS_M; ++k) dmax = fmax(dmax, S[k * FS_LDS + k]);   // broadcast reads
   const double floor_ = dmax * 1e-10;
-  if (g == 0) { yrow[c] = y[0][0]; yrow[c + 64] = y[0][1]; }
-  if (sq == 0) col[si] = sreg[0];                                         // column 0 of S
-  __syncthreads();
-  for (int k = 0; k < FS_M; ++k) {
-    const double* ccur = col + (k & 1) * FS_M;
-    double* cnext = col + ((k + 1) & 1) * FS_M;
-    const double d = ccur[k];
-    if (!(d > floor_)) return false;
-    const double r = fs_rcp(d);
-    if (tid == 0) dsave[k] = d;
-    const double yk0 = yrow[(k & 1) * FS_N + c], yk1 = yrow[(k & 1) * FS_N + c + 64];
-    double pub0 = 0.0, pub1 = 0.0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int i = 4 * j + g;
-      if (i > k) {
-        const double mi = ccur[i] * r;
-        y[j][0] = fma(-mi, yk0, y[j][0]);
-        y[j][1] = fma(-mi, yk1, y[j][1]);
+  for (int kb = 0; kb < FS_M / 8; ++kb) {
+    const int k0 = 8 * kb;
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      const double d = S[k * FS_LDS + k];
+      if (!(d > floor_)) return false;                                   // uniform
+      const double rcp = fs_rcp(d);
+      if (tid == 0) dsave[k] = d;
+      // multipliers of this column (also kept for the trailing update)
+      if (tid < FS_M && tid > k) Lp[tid * FS_LDP + j] = S[tid * FS_LDS + k] * rcp;
+      // panel: S[i][c] -= (S[i][k] / d) S[c][k] for k < c < k0 + 8, i >= c
+      const int nc = 7 - j;                                              // remaining columns of the block
+      for (int e = tid; e < nc * FS_M; e += FS_THREADS) {
+        const int c = k + 1 + e / FS_M, i = e % FS_M;
+        if (i >= c) S[i * FS_LDS + c] = fma(-S[i * FS_LDS + k] * rcp, S[c * FS_LDS + k], S[i * FS_LDS + c]);
       }
-      if (i == k + 1) { pub0 = y[j][0]; pub1 = y[j][1]; }
+      // the block's remaining rows of Y: Y[k'] -= (S[k'][k] / d) Y[k]
+      for (int e = tid; e < nc * FS_N; e += FS_THREADS) {
+        const int kk = k + 1 + e / FS_N, col = e % FS_N;
+        Y[kk * FS_LDV + col] = fma(-S[kk * FS_LDS + k] * rcp, Y[k * FS_LDV + col], Y[kk * FS_LDV + col]);
+      }
+      __syncthreads();
     }
-    if (g == ((k + 1) & 3) && k + 1 < FS_M) {
-      yrow[((k + 1) & 1) * FS_N + c] = pub0;
-      yrow[((k + 1) & 1) * FS_N + c + 64] = pub1;
-    }
-    if (si > k) {                                                         // S[i][j] -= S[i][k] S[j][k] / d, k < j <= i
-      const double mi = ccur[si] * r;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int j = sq + 4 * u;
-        if (j > k && j <= si) sreg[u] = fma(-mi, ccur[j], sreg[u]);
-        if (j == k + 1 && j <= si) cnext[si] = sreg[u];
+    // rank-8 trailing update (rows and columns >= k0 + 8), DMMA: P = Lp[rows] . B with
+    //   B(j, col) = Y[k0 + j][col]  for the rows of Y,   B(j, c) = S[c][k0 + j]  (= l_cj d_j) for S
+    const int rt0 = kb + 1, nrt = FS_M / 8 - rt0;                        // row tiles rt0 .. 7
+    const int ny = nrt * (FS_N / 8), ns = nrt * (nrt + 1) / 2;
+    for (int t = warp; t < ny + ns; t += FS_WARPS) {
+      double c0 = 0.0, c1 = 0.0;
+      if (t < ny) {
+        const int rt = rt0 + t / (FS_N / 8), ct = t % (FS_N / 8);
+        const double* a = Lp + (8 * rt + r) * FS_LDP + c4;
+        const double* b = Y + (k0 + c4) * FS_LDV + 8 * ct + r;
+        dmma(c0, c1, a[0], b[0]);
+        dmma(c0, c1, a[4], b[4 * FS_LDV]);
+        double* o = Y + (8 * rt + r) * FS_LDV + 8 * ct + 2 * c4;
+        o[0] -= c0;
+        o[1] -= c1;
+      } else {
+        int u = t - ny, rt = 0;                                          // lower-triangular tile (rt, ct), ct <= rt
+        while (u > rt) { u -= rt + 1; ++rt; }
+        const int ct = rt0 + u;
+        rt += rt0;
+        const double* a = Lp + (8 * rt + r) * FS_LDP + c4;
+        const double* b = S + (8 * ct + r) * FS_LDS + k0 + c4;
+        dmma(c0, c1, a[0], b[0]);
+        dmma(c0, c1, a[4], b[4]);
+        double* o = S + (8 * rt + r) * FS_LDS + 8 * ct + 2 * c4;
+        o[0] -= c0;
+        o[1] -= c1;
       }
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const double sc = fs_rsqrt(dsave[4 * j + g]);
-    Out[(4 * j + g) * FS_LDV + c] = y[j][0] * sc;
-    Out[(4 * j + g) * FS_LDV + c + 64] = y[j][1] * sc;
+  if (tid < FS_M) dsave[tid] = fs_rsqrt(dsave[tid]);
+  __syncthreads();
+  for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) {
+    const int i = e >> 7, col = e & 127;
+    Out[i * FS_LDV + col] = Y[i * FS_LDV + col] * dsave[i];
   }
   return true;
 }
@@ -393,10 +409,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   double* Sm = fsm + FS_OFF_S;
   double* Wm = fsm + FS_OFF_W;
   double* misc = fsm + FS_OFF_MISC;
-  double *dsave = misc, *nrm2 = misc + 64, *yrow = misc + 128, *red = misc + 384, *lamv = misc + 416, *invn = misc + 480;
+  double *dsave = misc, *nrm2 = misc + 64, *red = misc + 384, *lamv = misc + 416, *invn = misc + 480;
   int* ord = reinterpret_cast<int*>(misc + 544);
   int* rot_count = reinterpret_cast<int*>(misc + 577);
-  double* scol = misc + 592;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   double* hdr = vt + (size_t)FS_N * FS_N;
   // phase clocks (diagnostics in the unused slots behind the singular values: info[4 + i] = cycles of phase i)
@@ -444,7 +459,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     fs_gemm_abt(A2, A2, Sm, warp, lane);               // S = Y Y^T
     __syncthreads();
     tick();                                            // 2
-    if (!fs_orthonormalize(Sm, A2, A1, yrow, scol, dsave, tid)) { fail(2, (double)iter); return; }   // Q = D^-1/2 L^-1 Y
+    if (!fs_orthonormalize_blocked(Sm, A2, A1, misc + 832, dsave, tid)) { fail(2, (double)iter); return; }   // Q = D^-1/2 L^-1 Y
     __syncthreads();
     tick();                                            // 3
     tick();                                            // 4
@@ -539,7 +554,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
   double* Sm = fsm + FS_OFF_S;
   double* Wm = fsm + FS_OFF_W;
   double* misc = fsm + FS_OFF_MISC;
-  double *dsave = misc, *yrow = misc + 128, *scol = misc + 592;
+  double* dsave = misc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (skip[2] == 0.0) return;                          // the ordinary pipeline ran: the buffer holds its full rotation
   for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) {
@@ -560,7 +575,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
   for (int round = 0; round < 2; ++round) {
     fs_gemm_abt(src, src, Wm, warp, lane);             // S = P P^T
     __syncthreads();
-    if (!fs_orthonormalize(Wm, src, dst, yrow, scol, dsave, tid)) {   // P <- D^-1/2 L^-1 P
+    if (!fs_orthonormalize_blocked(Wm, src, dst, misc + 832, dsave, tid)) {   // P <- D^-1/2 L^-1 P
       if (tid == 0) skip[1] = 1.0;
       return;
     }
