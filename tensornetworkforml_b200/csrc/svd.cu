@@ -1268,7 +1268,9 @@ constexpr int CHOL_BIG_CAP_256 = 100, CHOL_BIG_CAP_512 = 50;   // factor rows ca
 static cudaError_t jacobi_prepare() {
   cudaError_t e = cudaFuncSetAttribute(k_jacobi<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 8);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_fast_split, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_fast_split<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_fast_split<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(k_fast_complement, cudaFuncAttributeMaxDynamicSharedMemorySize, FS_SMEM_BYTES);
   if (e != cudaSuccess) return e;
@@ -1909,6 +1911,14 @@ static int fast_split_enabled() {   // TNML_FAST_SPLIT=0: never take the warm-st
   }
   return v;
 }
+static int fast_split_variant() {   // TNML_FAST_VARIANT: 1 = 256-thread CTA, four rotations per warp; 2 = 512 threads, two
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TNML_FAST_VARIANT");
+    v = (e && atoi(e) == 2) ? 2 : 1;
+  }
+  return v;
+}
 static bool fast_split_shape(int n, int m) { return n == FS_N && m == FS_M && fast_split_enabled(); }
 static bool fast_generic_shape(int n, int m) {
   return (n == 256 || n == 512) && 2 * m == n && fast_split_enabled() && jacobi_variant() == 2 && chol_big_enabled();
@@ -1960,7 +1970,10 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
     double* Gs = Y;                                   // the Y buffer is free until a second pass runs
     k_sum_partials<<<tnml_cdiv(n * n, 256), 256, 0, st>>>(partial, p.nparts, n, n, Gs, jb.flags, nullptr, 1, nullptr, 1);
     if (gram_done) cudaEventRecord(gram_done, st);
-    k_fast_split<<<1, FS_THREADS, FS_SMEM_BYTES, st>>>(Gs, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n);
+    if (fast_split_variant() == 2)
+      k_fast_split<512, 2><<<1, 512, FS_SMEM_BYTES, st>>>(Gs, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n);
+    else
+      k_fast_split<256, 1><<<1, 256, FS_SMEM_BYTES, st>>>(Gs, vt1, lam1, skip, (int*)(w + p.off_sub), svals + n);
     k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(Gs, 1, n, vt1, lam1, 40, tol_final, 1, 1, svals + n, skip1, nullptr,
                                                  nullptr, nullptr, nullptr, m, nullptr, 0LL, 0, skip + 2, warm_hdr);
     rc = tnml_launch_status();

@@ -23,8 +23,9 @@ namespace tnml {
 constexpr int FS_N = 128, FS_M = 64;
 constexpr int FS_LDV = FS_N + 4;   // row stride of the 64 x 128 panels (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int FS_LDS = FS_M + 4;   // row stride of the 64 x 64 matrices
-constexpr int FS_THREADS = 256;   // 8 warps: up to 255 registers per thread (the Jacobi blocks and the Y panel live there)
-constexpr int FS_WARPS = FS_THREADS / 32;
+// CTA size: 256 threads (8 warps, Jacobi with four rotations per warp) or 512 (16 warps, two rotations per warp: twice as
+// many, shorter dependency chains per scheduler); the helpers read blockDim.x.
+constexpr int FS_THREADS = 256;
 constexpr int FS_OFF_A1 = 0;
 constexpr int FS_OFF_A2 = FS_OFF_A1 + FS_M * FS_LDV;
 constexpr int FS_OFF_S = FS_OFF_A2 + FS_M * FS_LDV;
@@ -53,7 +54,7 @@ __device__ __forceinline__ double fs_rsqrt(double x) {   // x > 0, normal: MUFU 
 // global memory (L2): warp w owns the 8 output columns 8w .. 8w+7, i.e. 8 rows of G, read exactly once.
 __device__ __forceinline__ void fs_gemm_vg(const double* __restrict__ V, const double* __restrict__ G,
                                            double* __restrict__ Out, int warp_, int lane) {
- for (int warp = warp_; warp < 16; warp += FS_WARPS) {
+ for (int warp = warp_; warp < 16; warp += (int)(blockDim.x >> 5)) {
   const int r = lane >> 2, c = lane & 3;
   const double* g = G + (size_t)(warp * 8 + r) * FS_N + c;
   double acc[8][2];
@@ -87,7 +88,7 @@ __device__ __forceinline__ void fs_gemm_vg(const double* __restrict__ V, const d
 // C[i][j] = sum_{k < 128} A[i][k] B[j][k], i, j < 64 (A, B: stride FS_LDV; C: stride FS_LDS).  16 warps x 4 tiles.
 __device__ __forceinline__ void fs_gemm_abt(const double* __restrict__ A, const double* __restrict__ B,
                                             double* __restrict__ C, int warp_, int lane) {
- for (int warp = warp_; warp < 16; warp += FS_WARPS) {
+ for (int warp = warp_; warp < 16; warp += (int)(blockDim.x >> 5)) {
   const int r = lane >> 2, c = lane & 3;
   const int ib = warp >> 1, jh = warp & 1;
   double acc[4][2];
@@ -115,7 +116,7 @@ __device__ __forceinline__ void fs_gemm_abt(const double* __restrict__ A, const 
 template <class Epi>
 __device__ __forceinline__ void fs_gemm_ab(const double* __restrict__ A, const int* __restrict__ rowmap,
                                            const double* __restrict__ B, int warp_, int lane, Epi epi) {
- for (int warp = warp_; warp < 16; warp += FS_WARPS) {
+ for (int warp = warp_; warp < 16; warp += (int)(blockDim.x >> 5)) {
   const int r = lane >> 2, c = lane & 3;
   const int ib = warp >> 1, jh = warp & 1;
   double acc[8][2];
@@ -181,12 +182,12 @@ __device__ __forceinline__ bool fs_orthonormalize_blocked(double* __restrict__ S
       if (tid < FS_M && tid > k) Lp[tid * FS_LDP + j] = S[tid * FS_LDS + k] * rcp;
       // panel: S[i][c] -= (S[i][k] / d) S[c][k] for k < c < k0 + 8, i >= c
       const int nc = 7 - j;                                              // remaining columns of the block
-      for (int e = tid; e < nc * FS_M; e += FS_THREADS) {
+      for (int e = tid; e < nc * FS_M; e += (int)blockDim.x) {
         const int c = k + 1 + e / FS_M, i = e % FS_M;
         if (i >= c) S[i * FS_LDS + c] = fma(-S[i * FS_LDS + k] * rcp, S[c * FS_LDS + k], S[i * FS_LDS + c]);
       }
       // the block's remaining rows of Y: Y[k'] -= (S[k'][k] / d) Y[k]
-      for (int e = tid; e < nc * FS_N; e += FS_THREADS) {
+      for (int e = tid; e < nc * FS_N; e += (int)blockDim.x) {
         const int kk = k + 1 + e / FS_N, col = e % FS_N;
         Y[kk * FS_LDV + col] = fma(-S[kk * FS_LDS + k] * rcp, Y[k * FS_LDV + col], Y[kk * FS_LDV + col]);
       }
@@ -196,7 +197,7 @@ __device__ __forceinline__ bool fs_orthonormalize_blocked(double* __restrict__ S
     //   B(j, col) = Y[k0 + j][col]  for the rows of Y,   B(j, c) = S[c][k0 + j]  (= l_cj d_j) for S
     const int rt0 = kb + 1, nrt = FS_M / 8 - rt0;                        // row tiles rt0 .. 7
     const int ny = nrt * (FS_N / 8), ns = nrt * (nrt + 1) / 2;
-    for (int t = warp; t < ny + ns; t += FS_WARPS) {
+    for (int t = warp; t < ny + ns; t += (int)(blockDim.x >> 5)) {
       double c0 = 0.0, c1 = 0.0;
       if (t < ny) {
         const int rt = rt0 + t / (FS_N / 8), ct = t % (FS_N / 8);
@@ -225,7 +226,7 @@ __device__ __forceinline__ bool fs_orthonormalize_blocked(double* __restrict__ S
   }
   if (tid < FS_M) dsave[tid] = fs_rsqrt(dsave[tid]);
   __syncthreads();
-  for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) {
+  for (int e = tid; e < FS_M * FS_N; e += (int)blockDim.x) {
     const int i = e >> 7, col = e & 127;
     Out[i * FS_LDV + col] = Y[i * FS_LDV + col] * dsave[i];
   }
@@ -304,7 +305,7 @@ __device__ __forceinline__ int fs_jacobi_rows(double* __restrict__ X, double* __
                                               int max_sweeps, double tol2, int tid) {
   constexpr int NP = FS_M, LD = FS_LDS, NB = NP / 4, NW = NB / 2, E = NP / 32;
   const int warp = tid >> 5, lane = tid & 31;
-  const bool act = warp < NW;     // (every warp when FS_THREADS == 256)
+  const bool act = warp < NW;     // (every warp of a 256-thread CTA)
   int sweeps_done = 0;
   int ra = (warp == 0) ? 0 : warp - 1, rb = NB - 2 - warp;
   if (tid == 0) *rot_count = 0;
@@ -398,9 +399,148 @@ __device__ __forceinline__ int fs_jacobi_rows(double* __restrict__ X, double* __
   return sweeps_done;
 }
 
-// One CTA of FS_THREADS threads.  G: n x n Gram matrix (global); vt: warm buffer (n x n rows = vectors, then FS_HDR
+// Two rotations per warp (lanes 0-15 / 16-31 compute the parameters of rotation 0 / 1), otherwise like rotate4_lanes.
+template <int E>
+__device__ __forceinline__ bool rotate2_lanes(double (&x)[2][E], double (&y)[2][E], double (&nx)[2], double (&ny)[2],
+                                              double tol2, int lane) {
+  double g[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      if (k & 1) a1 = fma(x[i][k], y[i][k], a1);
+      else a0 = fma(x[i][k], y[i][k], a0);
+    }
+    g[i] = a0 + a1;
+  }
+  const bool hi = lane & 16;
+  double ga = hi ? g[1] : g[0];
+  ga += __shfl_xor_sync(0xffffffffu, hi ? g[0] : g[1], 16);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 8);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 4);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 2);
+  ga += __shfl_xor_sync(0xffffffffu, ga, 1);                   // rotation (lane >> 4)'s inner product
+  const double al = hi ? nx[1] : nx[0];
+  const double be = hi ? ny[1] : ny[0];
+  const int ex = (__double2hiint(al + be) >> 20) & 0x7ff;
+  const double g2 = ga * ga, ab = al * be;
+  const bool rot = (g2 > tol2 * ab) && ex > 0 && ex < 2040;
+  const double sc = __hiloint2double((2046 - ex) << 20, 0);
+  const float df = (float)((be - al) * sc), tf = (float)((ga + ga) * sc);
+  const float hh = fmaf(df, df, tf * tf);
+  const float h = hh * rsqrt_approx(hh);
+  const float t0 = __fdividef(tf, df + copysignf(h, df));
+  const float cf = rsqrt_approx(fmaf(t0, t0, 1.0f));
+  const double c = (double)cf, sv = (double)(cf * t0);
+  const double e = fma(c, c, fma(sv, sv, -1.0));
+  const double nu = fma(e, fma(e, 0.375, -0.5), 1.0);
+  const double cj = rot ? c * nu : 1.0;
+  const double sj = rot ? sv * nu : 0.0;
+  const double tj = rot ? (double)t0 * ga : 0.0;
+  const bool any = __any_sync(0xffffffffu, rot && (g2 > 1e-16 * ab));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double cs = __shfl_sync(0xffffffffu, cj, 16 * i), sn = __shfl_sync(0xffffffffu, sj, 16 * i);
+    const double tg = __shfl_sync(0xffffffffu, tj, 16 * i);
+    nx[i] -= tg;
+    ny[i] += tg;
+#pragma unroll
+    for (int k = 0; k < E; ++k) {
+      const double a = x[i][k], b = y[i][k];
+      x[i][k] = fma(cs, a, -sn * b);
+      y[i][k] = fma(sn, a, cs * b);
+    }
+  }
+  return any;
+}
+
+// The same sweeps for a 512-thread CTA: blocks of TWO rows, sixteen warps, each owns one block pair per block-round (31
+// rounds) and performs its 4 cross rotations in two sets of two (plus, in the first round, the pair inside each block).
+// Per rotation set a warp's dependency chain is ~115 instead of ~170 instructions and every scheduler interleaves four
+// such chains instead of two.
+__device__ __forceinline__ int fs_jacobi_rows2(double* __restrict__ X, double* __restrict__ nrm2, int max_sweeps,
+                                               double tol2, int tid) {
+  constexpr int NP = FS_M, LD = FS_LDS, NB = NP / 2, NW = NB / 2, E = NP / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  int sweeps_done = 0;
+  int ra = (warp == 0) ? 0 : warp - 1, rb = NB - 2 - warp;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    for (int r = warp; r < NP; r += NW) {   // refresh the cached squared row norms
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const double v = X[r * LD + lane + 32 * k]; s = fma(v, v, s); }
+      s = warp_sum(s);
+      if (lane == 0) nrm2[r] = s;
+    }
+    __syncthreads();
+    bool rotated = false;
+    for (int round = 0; round < NB - 1; ++round) {
+      const int bi = (warp == 0) ? 0 : 1 + ra;
+      const int bj = 1 + rb;
+      double a[2][E], b[2][E], na[2], nb[2];
+      double* const wa = X + 2 * bi * LD + lane;
+      double* const wb = X + 2 * bj * LD + lane;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          a[i][k] = wa[i * LD + 32 * k];
+          b[i][k] = wb[i * LD + 32 * k];
+        }
+        na[i] = nrm2[2 * bi + i];
+        nb[i] = nrm2[2 * bj + i];
+      }
+      if (round == 0) {   // the pair inside each block, once per sweep
+        double x[2][E], y[2][E], nx[2], ny[2];
+#pragma unroll
+        for (int k = 0; k < E; ++k) { x[0][k] = a[0][k]; y[0][k] = a[1][k]; x[1][k] = b[0][k]; y[1][k] = b[1][k]; }
+        nx[0] = na[0]; ny[0] = na[1]; nx[1] = nb[0]; ny[1] = nb[1];
+        rotated |= rotate2_lanes<E>(x, y, nx, ny, tol2, lane);
+#pragma unroll
+        for (int k = 0; k < E; ++k) { a[0][k] = x[0][k]; a[1][k] = y[0][k]; b[0][k] = x[1][k]; b[1][k] = y[1][k]; }
+        na[0] = nx[0]; na[1] = ny[0]; nb[0] = nx[1]; nb[1] = ny[1];
+      }
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {   // the 4 pairs across the two blocks: set s pairs a[i] with b[(i+s)&1]
+        double y[2][E], ny[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) y[i][k] = b[(i + s) & 1][k];
+          ny[i] = nb[(i + s) & 1];
+        }
+        rotated |= rotate2_lanes<E>(a, y, na, ny, tol2, lane);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+          for (int k = 0; k < E; ++k) b[(i + s) & 1][k] = y[i][k];
+          nb[(i + s) & 1] = ny[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int k = 0; k < E; ++k) {
+          wa[i * LD + 32 * k] = a[i][k];
+          wb[i * LD + 32 * k] = b[i][k];
+        }
+        if (lane == 0) { nrm2[2 * bi + i] = na[i]; nrm2[2 * bj + i] = nb[i]; }
+      }
+      ra = (ra + 1 == NB - 1) ? 0 : ra + 1;
+      rb = (rb + 1 == NB - 1) ? 0 : rb + 1;
+      __syncthreads();
+    }
+    sweeps_done = sweep + 1;
+    if (!__syncthreads_or(rotated ? 1 : 0)) break;
+  }
+  return sweeps_done;
+}
+
+// One CTA of NT threads (JV = 1: 256 threads, fs_jacobi_rows; JV = 2: 512 threads, fs_jacobi_rows2).  G: n x n Gram matrix (global); vt: warm buffer (n x n rows = vectors, then FS_HDR
 // doubles); lam: n eigenvalues out; skip: {second pass skipped, tail pass skipped, fast path taken}; sub: {ns, k0}.
-__global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __restrict__ G, double* __restrict__ vt,
+template <int NT, int JV>
+__global__ void __launch_bounds__(NT, 1) k_fast_split(const double* __restrict__ G, double* __restrict__ vt,
                                                               double* __restrict__ lam, double* __restrict__ skip,
                                                               int* __restrict__ sub, double* __restrict__ info) {
   extern __shared__ __align__(16) double fsm[];
@@ -436,7 +576,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
   };
   if (!(hdr[0] == 1.0 && hdr[1] == (double)FS_N && hdr[2] == (double)FS_M)) { fail(1, hdr[0]); return; }   // uniform
   // V0 = rows 0 .. m-1 of the warm buffer
-  for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) A1[(e >> 7) * FS_LDV + (e & 127)] = vt[e];
+  for (int e = tid; e < FS_M * FS_N; e += (int)blockDim.x) A1[(e >> 7) * FS_LDV + (e & 127)] = vt[e];
   // trace of G (warp 0)
   if (warp == 0) {
     double s = 0.0;
@@ -469,7 +609,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     fs_gemm_abt(A1, A2, Sm, warp, lane);               // T = Q Z^T
     __syncthreads();
     tick();                                            // 6
-    for (int e = tid; e < FS_M * FS_M; e += FS_THREADS) {   // symmetrise
+    for (int e = tid; e < FS_M * FS_M; e += (int)blockDim.x) {   // symmetrise
       const int i = e >> 6, j = e & 63;
       if (i < j) {
         const double v = 0.5 * (Sm[i * FS_LDS + j] + Sm[j * FS_LDS + i]);
@@ -487,7 +627,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     if (lane == 0) red[warp] = part;
     __syncthreads();
     resid2 = 0.0;
-    for (int w = 0; w < FS_THREADS / 32; ++w) resid2 += red[w];
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) resid2 += red[w];
     trT = 0.0;
     mind = 1e300;
     for (int k = 0; k < FS_M; ++k) { const double d = Sm[k * FS_LDS + k]; trT += d; mind = fmin(mind, d); }
@@ -499,11 +639,12 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_split(const double* __re
     resid2_prev = resid2;
   }
   if (!ok) { fail(3, mind > 0.0 ? sqrt(resid2) / mind : -1.0); return; }
-  const int sweeps = fs_jacobi_rows(Sm, nrm2, rot_count, 30, 64.0 * 4.930380657631324e-32, tid);
+  const int sweeps = JV == 2 ? fs_jacobi_rows2(Sm, nrm2, 30, 64.0 * 4.930380657631324e-32, tid)
+                             : fs_jacobi_rows(Sm, nrm2, rot_count, 30, 64.0 * 4.930380657631324e-32, tid);
   tphase = 8;
   tick();                                              // 8: Jacobi
   // rows of Sm are now lambda_k w_k^T: eigenvalue = row norm; rank them (descending, ties by index)
-  for (int r = warp; r < FS_M; r += FS_THREADS / 32) {
+  for (int r = warp; r < FS_M; r += (int)(blockDim.x >> 5)) {
     const double v0 = Sm[r * FS_LDS + lane], v1 = Sm[r * FS_LDS + lane + 32];
     const double s = warp_sum(fma(v0, v0, v1 * v1));
     if (lane == 0) { const double nr = sqrt(s); lamv[r] = nr; invn[r] = nr > 0.0 ? 1.0 / nr : 0.0; }
@@ -557,7 +698,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
   double* dsave = misc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (skip[2] == 0.0) return;                          // the ordinary pipeline ran: the buffer holds its full rotation
-  for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) {
+  for (int e = tid; e < FS_M * FS_N; e += (int)blockDim.x) {
     A1[(e >> 7) * FS_LDV + (e & 127)] = vt[e];                              // Q
     A2[(e >> 7) * FS_LDV + (e & 127)] = vt[(size_t)FS_M * FS_N + e];        // P0
   }
@@ -582,7 +723,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fast_complement(double* __res
     __syncthreads();
     double* t = src; src = dst; dst = t;
   }
-  for (int e = tid; e < FS_M * FS_N; e += FS_THREADS) vt[(size_t)FS_M * FS_N + e] = src[(e >> 7) * FS_LDV + (e & 127)];
+  for (int e = tid; e < FS_M * FS_N; e += (int)blockDim.x) vt[(size_t)FS_M * FS_N + e] = src[(e >> 7) * FS_LDV + (e & 127)];
 }
 
 __global__ void k_warm_header(double* __restrict__ hdr, int n, int m, const double* __restrict__ fastf) {
