@@ -105,7 +105,8 @@ int tnml_site_predict(const void* Lenv, const void* phi_p, const void* A_label, 
  * q[b][l][2*sigma+tau] = g[b][l] * phi_p[b][sigma] * phi_q[b][tau]   (operand of the gradient GEMM)
  * pp[b][2*sigma+tau]   = phi_p[b][sigma] * phi_q[b][tau]             (operand of the projection epilogue)
  * metrics[0] = number of samples with argmax(fa) == y, metrics[1] = sum |onehot(y) - fa|   (NC:697-702),
- * metrics[2] = Ns (the local sample count, so that the sharded sums can be all-reduced as they are), metrics[3] = 0
+ * metrics[2] = Ns (the local sample count, so that the sharded sums can be all-reduced as they are),
+ * metrics[3] = sum |f| (NC:744, debug history)
  * The two sums are reduced in a fixed order (deterministic).  ws: tnml_act_lossder_workspace_bytes(Ns). */
 int64_t tnml_act_lossder_workspace_bytes(int64_t Ns);
 int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const void* phi_q, void* q, void* pp,
@@ -145,8 +146,8 @@ int tnml_project(const void* B, const void* pp, const void* Lenv, const void* Re
  *                    gradient, so the caller may run it on another stream while tnml_grad runs.
  * tnml_bond_update : reg = L2_flag ? 2 wd G : wd B                                       NC:728-734, NC:1176
  *                    dB -= reg ; if sum|dB| > sum|B| : dB /= (sum|dB| / sum|B|) ; B' = B + lr dB     NC:755-761
- * stats[0..5] = { sum|B|, sum|dB| (after reg, before clip), wd*<B, G> (0 if !L2_flag), clipped?,
- *                 mean|B|, mean|dB| }                                     (NC:741-747 debug history)
+ * stats[0..7] = { sum|B|, sum|dB| (after reg, before clip), wd*<B, G> (0 if !L2_flag), clipped?,
+ *                 mean|B|, mean|dB|, mean|reg|, 0 }                       (NC:741-747 debug history)
  * G is ignored when !L2_flag.  Bnew may alias neither B nor dB.  All sums are fixed-order (deterministic). */
 int tnml_l2_term(const void* B, const void* EL, const void* ER, void* G, void* ws, int32_t Dl, int32_t Dr, int32_t L,
                  int32_t dtype, tnml_stream_t stream);

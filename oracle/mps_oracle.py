@@ -393,7 +393,9 @@ class OracleMPS:
             l2_loss, l2_grad = l2_term(B, self._norm[p], self._norm[q + 1], weight_dec)
             dB = dB - l2_grad
         else:
-            dB = dB - weight_dec * B
+            l2_grad = weight_dec * B                                          # NC:731-734
+            dB = dB - l2_grad
+        absreg = float(np.abs(l2_grad).mean())                                # NC:747 (debug history)
         absB, absdB = float(np.abs(B).mean()), float(np.abs(dB).mean())       # NC:741-742 (debug history)
         Bn = clip_and_update(B, dB, lr)                                       # NC:755-761
         f_new = project(Bn, Lenv, X[:, p, :], X[:, q, :], Renv)                # NC:494-523 (UN-truncated B')
@@ -414,7 +416,7 @@ class OracleMPS:
             self.sites[p] = A_left                                            # (a,s,l,m) label site
             self.sites[q] = A_right
             self.l_pos -= 1                                                   # NC:570-571
-        self.hist.append(dict(acc=acc, mae=mae, S=Svals, m=m, l2_loss=l2_loss, absB=absB, absdB=absdB,
+        self.hist.append(dict(acc=acc, mae=mae, S=Svals, m=m, l2_loss=l2_loss, absB=absB, absdB=absdB, absreg=absreg,
                               absf=float(np.abs(f).mean())))
         return f_new
 

@@ -365,10 +365,10 @@ class Network():
                     var_hist[0].append(h["stats"][i, 4])
                     var_hist[1].append(h["stats"][i, 5])
                     var_hist[2].append(h["acc"][i])
-                    var_hist[3].append(np.nan)
+                    var_hist[3].append(h["absf"][i])
                     var_hist[4].append(h["mae"][i])
                     var_hist[5].append(h["stats"][i, 2])
-                    var_hist[6].append(np.nan)
+                    var_hist[6].append(h["stats"][i, 6])
                 else:                                                   # NC:749-750
                     var_hist[0].append(h["acc"][i])
                     var_hist[1].append(h["mae"][i])
@@ -423,8 +423,8 @@ class Network():
             if debug:
                 if not L2_flag:
                     raise NameError("name 'L2_loss_term' is not defined")     # the reference's latent bug, NC:746
-                for row, val in enumerate((h["stats"][0, 4], h["stats"][0, 5], h["acc"][0], np.nan, h["mae"][0],
-                                           h["stats"][0, 2], np.nan)):
+                for row, val in enumerate((h["stats"][0, 4], h["stats"][0, 5], h["acc"][0], h["absf"][0], h["mae"][0],
+                                           h["stats"][0, 2], h["stats"][0, 6])):
                     var_hist[row].append(val)
             else:
                 var_hist[0].append(h["acc"][0])

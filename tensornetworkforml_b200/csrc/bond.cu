@@ -106,16 +106,16 @@ static int launch_gemm(int tA, int tB, int M, int N, int K, double alpha, const 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// bond update, stage 1: d = dB - reg, block partial sums of |B|, |d|, <B, G>
+// bond update, stage 1: d = dB - reg, block partial sums of |B|, |d|, <B, G>, |reg|
 // ---------------------------------------------------------------------------------------------------
 constexpr int BU_THREADS = 256;
 
 __global__ void __launch_bounds__(BU_THREADS) k_bu_partial(const double* __restrict__ B, const double* __restrict__ dB,
                                                           const double* __restrict__ G, double* __restrict__ D,
                                                           double* __restrict__ partial, int n, double wd, int L2_flag) {
-  __shared__ double red[3][BU_THREADS];
+  __shared__ double red[4][BU_THREADS];
   int e = blockIdx.x * BU_THREADS + threadIdx.x;
-  double sb = 0.0, sd = 0.0, sg = 0.0;
+  double sb = 0.0, sd = 0.0, sg = 0.0, sr = 0.0;
   if (e < n) {
     double b = B[e];
     double reg, gg = 0.0;
@@ -123,21 +123,22 @@ __global__ void __launch_bounds__(BU_THREADS) k_bu_partial(const double* __restr
     else reg = wd * b;                                // NC:733
     double d = dB[e] - reg;                          // NC:730 / NC:734
     D[e] = d;
-    sb = fabs(b); sd = fabs(d); sg = b * gg;
+    sb = fabs(b); sd = fabs(d); sg = b * gg; sr = fabs(reg);   // |reg|: debug history, NC:747
   }
-  red[0][threadIdx.x] = sb; red[1][threadIdx.x] = sd; red[2][threadIdx.x] = sg;
+  red[0][threadIdx.x] = sb; red[1][threadIdx.x] = sd; red[2][threadIdx.x] = sg; red[3][threadIdx.x] = sr;
   __syncthreads();
   for (int s = BU_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
 #pragma unroll
-      for (int r = 0; r < 3; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
+      for (int r = 0; r < 4; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    partial[3 * blockIdx.x] = red[0][0];
-    partial[3 * blockIdx.x + 1] = red[1][0];
-    partial[3 * blockIdx.x + 2] = red[2][0];
+    partial[4 * blockIdx.x] = red[0][0];
+    partial[4 * blockIdx.x + 1] = red[1][0];
+    partial[4 * blockIdx.x + 2] = red[2][0];
+    partial[4 * blockIdx.x + 3] = red[3][0];
   }
 }
 
@@ -146,21 +147,21 @@ __global__ void __launch_bounds__(BU_THREADS) k_bu_apply(const double* __restric
                                                         const double* __restrict__ partial, int nblocks,
                                                         double* __restrict__ Bnew, double* __restrict__ stats, int n,
                                                         double lr, double wd) {
-  __shared__ double red[3][BU_THREADS];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  __shared__ double red[4][BU_THREADS];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   for (int i = threadIdx.x; i < nblocks; i += BU_THREADS) {
-    s0 += partial[3 * i]; s1 += partial[3 * i + 1]; s2 += partial[3 * i + 2];
+    s0 += partial[4 * i]; s1 += partial[4 * i + 1]; s2 += partial[4 * i + 2]; s3 += partial[4 * i + 3];
   }
-  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2;
+  red[0][threadIdx.x] = s0; red[1][threadIdx.x] = s1; red[2][threadIdx.x] = s2; red[3][threadIdx.x] = s3;
   __syncthreads();
   for (int s = BU_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
 #pragma unroll
-      for (int r = 0; r < 3; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
+      for (int r = 0; r < 4; ++r) red[r][threadIdx.x] += red[r][threadIdx.x + s];
     }
     __syncthreads();
   }
-  const double sumB = red[0][0], sumD = red[1][0], l2 = red[2][0];
+  const double sumB = red[0][0], sumD = red[1][0], l2 = red[2][0], sumR = red[3][0];
   const bool clip = sumD > sumB;  // NC:756
   const double ratio = clip ? sumD / sumB : 1.0;
   int e = blockIdx.x * BU_THREADS + threadIdx.x;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(BU_THREADS) k_bu_apply(const double* __restric
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     stats[0] = sumB; stats[1] = sumD; stats[2] = wd * l2; stats[3] = clip ? 1.0 : 0.0;
-    stats[4] = sumB / n; stats[5] = sumD / n;
+    stats[4] = sumB / n; stats[5] = sumD / n; stats[6] = sumR / n; stats[7] = 0.0;
   }
 }
 
@@ -211,7 +212,7 @@ extern "C" int tnml_l2_term(const void* B, const void* EL, const void* ER, void*
 
 extern "C" int64_t tnml_bond_update_workspace_bytes(int32_t Dl, int32_t Dr, int32_t L) {
   int64_t n = (int64_t)Dl * 4 * L * Dr;
-  return (n + 3 * (int64_t)tnml_cdiv(n, BU_THREADS)) * 8;
+  return (n + 4 * (int64_t)tnml_cdiv(n, BU_THREADS)) * 8;
 }
 
 extern "C" int tnml_bond_update(const void* B, const void* dB, const void* G, void* Bnew, void* stats, void* ws,

@@ -141,9 +141,9 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
                                                         const float2* __restrict__ phi_q, float* __restrict__ g,
                                                         float* __restrict__ pp, double* __restrict__ partial, int64_t Ns,
                                                         int L, int act, int loss, double T) {
-  __shared__ double red[2][256];
+  __shared__ double red[3][256];
   const int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  double n_ok = 0.0, abs_err = 0.0;
+  double n_ok = 0.0, abs_err = 0.0, abs_f = 0.0;
   if (b < Ns) {
     const float* fb = f + b * L;
     const int yb = y[b];
@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
     for (int l = 0; l < L; ++l) {
       const double v = fb[l];
       double fa;
+      abs_f += fabs(v);
       if (act == TNML_ACT_LINEAR) fa = v;
       else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));
       else fa = exp((v - shift) / T) / denom;
@@ -182,32 +183,39 @@ __global__ void __launch_bounds__(256) k_act_lossder_f32(const float* __restrict
   }
   red[0][threadIdx.x] = n_ok;
   red[1][threadIdx.x] = abs_err;
+  red[2][threadIdx.x] = abs_f;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       red[0][threadIdx.x] += red[0][threadIdx.x + s];
       red[1][threadIdx.x] += red[1][threadIdx.x + s];
+      red[2][threadIdx.x] += red[2][threadIdx.x + s];
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    partial[2 * blockIdx.x] = red[0][0];
-    partial[2 * blockIdx.x + 1] = red[1][0];
+    partial[3 * blockIdx.x] = red[0][0];
+    partial[3 * blockIdx.x + 1] = red[1][0];
+    partial[3 * blockIdx.x + 2] = red[2][0];
   }
 }
 
 __global__ void __launch_bounds__(256) k_metrics_final_f32(const double* __restrict__ partial, int nblocks,
                                                           double* __restrict__ metrics, double count) {
-  __shared__ double red[2][256];
-  double a = 0.0, e = 0.0;
-  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; e += partial[2 * i + 1]; }
-  red[0][threadIdx.x] = a; red[1][threadIdx.x] = e;
+  __shared__ double red[3][256];
+  double a = 0.0, e = 0.0, af = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[3 * i]; e += partial[3 * i + 1]; af += partial[3 * i + 2]; }
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = e; red[2][threadIdx.x] = af;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+    if (threadIdx.x < s) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + s];
+      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+      red[2][threadIdx.x] += red[2][threadIdx.x + s];
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = 0.0; }
+  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = red[2][0]; }
 }
 
 // f[b][l] = sum L[b][a] phi[b][s] A[a][s][l][c] R[b][c]; thin kernel (forward() calls it with Dl == 1 or Dr == 1)

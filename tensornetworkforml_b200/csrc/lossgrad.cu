@@ -16,9 +16,9 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
                                                            const double2* __restrict__ phi_q, double* __restrict__ q,
                                                            double* __restrict__ pp, double* __restrict__ partial,
                                                            int64_t Ns, int L, int act, int loss, double T) {
-  __shared__ double red[2][AL_THREADS];
+  __shared__ double red[3][AL_THREADS];
   const int64_t b = (int64_t)blockIdx.x * AL_THREADS + threadIdx.x;
-  double n_ok = 0.0, abs_err = 0.0;
+  double n_ok = 0.0, abs_err = 0.0, abs_f = 0.0;
   if (b < Ns) {
     const double* fb = f + b * L;
     const int yb = y[b];
@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
     int arg = 0;
     for (int l = 0; l < L; ++l) {
       double v = fb[l], fa;
+      abs_f += fabs(v);                                   // NC:744 (debug history: mean |f_orig|)
       if (act == TNML_ACT_LINEAR) fa = v;
       else if (act == TNML_ACT_SIGMOID) fa = 1.0 / (1.0 + exp(-v / T));  // NC:791
       else fa = exp((v - shift) / T) / denom;
@@ -58,17 +59,20 @@ __global__ void __launch_bounds__(AL_THREADS) k_act_lossder(const double* __rest
   }
   red[0][threadIdx.x] = n_ok;
   red[1][threadIdx.x] = abs_err;
+  red[2][threadIdx.x] = abs_f;
   __syncthreads();
   for (int s = AL_THREADS / 2; s > 0; s >>= 1) {
     if (threadIdx.x < s) {
       red[0][threadIdx.x] += red[0][threadIdx.x + s];
       red[1][threadIdx.x] += red[1][threadIdx.x + s];
+      red[2][threadIdx.x] += red[2][threadIdx.x + s];
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    partial[2 * blockIdx.x] = red[0][0];
-    partial[2 * blockIdx.x + 1] = red[1][0];
+    partial[3 * blockIdx.x] = red[0][0];
+    partial[3 * blockIdx.x + 1] = red[1][0];
+    partial[3 * blockIdx.x + 2] = red[2][0];
   }
 }
 
@@ -113,16 +117,20 @@ __global__ void __launch_bounds__(256) k_loss_der(const double* __restrict__ fa,
 // fixed-order final sum of the per-block partials (one block)
 __global__ void __launch_bounds__(256) k_metrics_final(const double* __restrict__ partial, int nblocks,
                                                       double* __restrict__ metrics, double count) {
-  __shared__ double red[2][256];
-  double a = 0.0, e = 0.0;
-  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[2 * i]; e += partial[2 * i + 1]; }
-  red[0][threadIdx.x] = a; red[1][threadIdx.x] = e;
+  __shared__ double red[3][256];
+  double a = 0.0, e = 0.0, af = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += 256) { a += partial[3 * i]; e += partial[3 * i + 1]; af += partial[3 * i + 2]; }
+  red[0][threadIdx.x] = a; red[1][threadIdx.x] = e; red[2][threadIdx.x] = af;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
-    if (threadIdx.x < s) { red[0][threadIdx.x] += red[0][threadIdx.x + s]; red[1][threadIdx.x] += red[1][threadIdx.x + s]; }
+    if (threadIdx.x < s) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + s];
+      red[1][threadIdx.x] += red[1][threadIdx.x + s];
+      red[2][threadIdx.x] += red[2][threadIdx.x + s];
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = 0.0; }
+  if (threadIdx.x == 0) { metrics[0] = red[0][0]; metrics[1] = red[1][0]; metrics[2] = count; metrics[3] = red[2][0]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -272,7 +280,7 @@ static void grad_plan(int64_t Ns, int Dl, int Dr, int L, int* cols, int* ks, int
 using namespace tnml;
 
 extern "C" int64_t tnml_act_lossder_workspace_bytes(int64_t Ns) {
-  return (int64_t)tnml_cdiv(Ns, AL_THREADS) * 2 * 8;
+  return (int64_t)tnml_cdiv(Ns, AL_THREADS) * 3 * 8;
 }
 
 extern "C" int tnml_act_lossder(const void* f, const int32_t* y, const void* phi_p, const void* phi_q, void* q, void* pp,

@@ -451,7 +451,7 @@ class SweepEngine:
         self.hist = dict(tail_recs=torch.zeros((nsteps, rec_doubles), dtype=torch.float64, device=self.device),
                          tail_solved=0,
                          metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
-                         stats=torch.zeros((nsteps, 6), dtype=torch.float64, device=self.device),
+                         stats=torch.zeros((nsteps, 8), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
                          nsv=[], m=[], n=0, fast_keys=[], fast_seen=0)
         self.hist["tail_recs"][:, 1] = 1.0            # "nothing recorded" until a tail call writes the header
@@ -569,7 +569,7 @@ class SweepEngine:
         if side is not main:
             main.wait_stream(side)                      # B and G are ready
         ws = self._workspace("bu", self._ws_bytes("tnml_bond_update_workspace_bytes", Dl, Dr, L))
-        call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 6 * 8,
+        call("tnml_bond_update", _ptr(B), _ptr(dB), _ptr(G), _ptr(Bn), self.hist["stats"].data_ptr() + step * 8 * 8,
              _ptr(ws), Dl, Dr, L, float(lr), float(weight_dec), 1 if L2_flag else 0, F64, st)
         self._inflight = (B, Bn, dB, G)
         return dict(B=B, Bn=Bn, G=G, p=p, q=q, Dl=Dl, Dr=Dr, nB=nB, left_dir=left_dir, step=step, main=main, side=side)
@@ -728,6 +728,7 @@ class SweepEngine:
         total = met[:, 2]
         acc = met[:, 0] / total                                   # NC:700
         mae = met[:, 1] / (total * self.L)                        # NC:702
+        absf = met[:, 3] / (total * self.L)                       # NC:744 (debug history: mean |f_orig|)
         svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
         fk = self.hist["fast_keys"]
         for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)
@@ -745,7 +746,7 @@ class SweepEngine:
             self._warm_fail[ent[1]] = fails
             self._warm_wait[ent[1]] = 0 if fails < 2 else 2
         self.hist["fast_seen"] = len(fk)
-        return dict(acc=acc, mae=mae, stats=stats, svals=svals, m=list(self.hist["m"]))
+        return dict(acc=acc, mae=mae, absf=absf, stats=stats, svals=svals, m=list(self.hist["m"]))
 
     def bond_dims(self):
         return list(self.bonds[1:self.S])

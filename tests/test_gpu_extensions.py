@@ -299,3 +299,23 @@ def test_device_side_generators(tn):
     f_dev = net.forward_raw(x[:500])
     f_host = net.forward(gen.psi(xh[:500].reshape(500, -1)))
     assert G.rel(f_dev.elem, f_host.elem) < 1e-13
+
+
+# ------------------------------------------------------------------------------------------- ADVICE (low)
+@pytest.mark.parametrize("L2", [True, False])
+def test_debug_history_has_all_seven_series(tn, L2):
+    """debug=True (NC:741-747): mean |B|, mean |dB|, accuracy, mean |f_orig|, MAE, L2 loss term, mean |L2 gradient| --
+    all from sums reduced on the device; with L2_flag=False the reference raises NameError (NC:746), and so do we."""
+    S, D, Lbl, Ns = 8, 5, 3, 150
+    X, y, orc, net = _pair(tn, S, D, Lbl, Ns, "linear", "MSE", 12, truncation="fixed", max_bond=D)
+    fo, f = orc.forward(X), net.forward(X)
+    vh = [[] for _ in range(7)]
+    if not L2:
+        with pytest.raises(NameError):
+            net.sweep(X, y, f, 0.02, 0.1, L2_flag=False, left_dir=False, var_hist=vh, debug=True)
+        return
+    orc.sweep(y, fo, 0.02, 0.1, True, False)
+    net.sweep(X, y, f, 0.02, 0.1, L2_flag=True, left_dir=False, var_hist=vh, debug=True)
+    for row, key in enumerate(("absB", "absdB", "acc", "absf", "mae", "l2_loss", "absreg")):
+        want = np.array([h[key] for h in orc.hist])
+        assert np.abs(np.array(vh[row]) - want).max() <= TOL * np.abs(want).max(), key

@@ -131,6 +131,7 @@ def test_act_lossder_metrics(L, act, loss):
     m = met.cpu().numpy()
     assert m[0] == round(acc * Ns)
     assert abs(m[1] / (Ns * nl) - mae) < 1e-13
+    assert m[2] == Ns and abs(m[3] - np.abs(f).sum()) < 1e-11 * np.abs(f).sum()      # NC:744 (debug history)
 
 
 GRAD_SHAPES = [(50, 1, 5, 2), (200, 4, 4, 3), (3000, 64, 64, 10), (777, 10, 2, 2), (100, 70, 3, 2), (90, 3, 130, 2),
@@ -204,7 +205,7 @@ def test_bond_update(L, Dl, Dr, nl, L2, scale):
     a, c = rng.standard_normal((Dl, Dl)), rng.standard_normal((Dr, Dr))
     EL, ER = a @ a.T, c @ c.T
     lr, wd = 0.05, 0.3
-    Bn, stats = empty(Dl, 2, nl, 2, Dr), empty(6)
+    Bn, stats = empty(Dl, 2, nl, 2, Dr), empty(8)
     ws = ws_for(L, "tnml_bond_update_workspace_bytes", Dl, Dr, nl)
     Bd, Gd, ws2 = dev(B), empty(Dl, 2, nl, 2, Dr), empty(Dl * 4 * nl * Dr)
     if L2:
@@ -225,6 +226,8 @@ def test_bond_update(L, Dl, Dr, nl, L2, scale):
     assert abs(s[1] - np.abs(d).sum()) < 1e-11 * np.abs(d).sum()
     assert abs(s[2] - loss) <= 1e-11 * abs(loss)
     assert s[3] == float(np.abs(d).sum() > np.abs(B).sum())
+    reg = g if L2 else wd * B
+    assert abs(s[6] - np.abs(reg).mean()) < 1e-11 * np.abs(reg).mean()      # NC:747 (debug history)
 
 
 @pytest.mark.parametrize("Dl,Dr", [(3, 5), (64, 64), (1, 4), (6, 1), (70, 20)])

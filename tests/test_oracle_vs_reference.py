@@ -60,7 +60,7 @@ def test_live_reference_three_sweeps(act, loss, L2, wd):
 
 
 def test_live_reference_debug_history_l2_term():
-    """debug var_hist rows (NC:741-747): |B|, |dB|, acc, |f|, MAE, L2 loss term."""
+    """debug var_hist rows (NC:741-747): |B|, |dB|, acc, |f|, MAE, L2 loss term, |L2 gradient|."""
     NC = _ref()
     S, M, L, Ns = 7, 4, 2, 32
     np.random.seed(5)
@@ -75,6 +75,6 @@ def test_live_reference_debug_history_l2_term():
     np.random.set_state(st)
     orc = O.OracleMPS.from_seed(S, M, L, calibration_X=X, normalize=True, act_fn="linear", loss_fn="MSE")
     orc.sweep(y, orc.forward(X), 0.01, 0.5, L2_flag=True, left_dir=False)
-    for row, key in ((0, "absB"), (1, "absdB"), (3, "absf"), (4, "mae"), (5, "l2_loss")):
+    for row, key in ((0, "absB"), (1, "absdB"), (3, "absf"), (4, "mae"), (5, "l2_loss"), (6, "absreg")):
         a = np.array([h[key] for h in orc.hist]); b = np.array(vh[row], dtype=np.float64).reshape(-1)
         assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max(), key
