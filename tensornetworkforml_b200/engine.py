@@ -726,9 +726,10 @@ class SweepEngine:
         stats = self.hist["stats"][:n].cpu().numpy()
         sv = self.hist["svals"][:n].cpu().numpy()
         total = met[:, 2]
-        acc = met[:, 0] / total                                   # NC:700
-        mae = met[:, 1] / (total * self.L)                        # NC:702
-        absf = met[:, 3] / (total * self.L)                       # NC:744 (debug history: mean |f_orig|)
+        with np.errstate(invalid="ignore", divide="ignore"):      # (a step without recorded metrics reads as nan)
+            acc = met[:, 0] / total                               # NC:700
+            mae = met[:, 1] / (total * self.L)                    # NC:702
+            absf = met[:, 3] / (total * self.L)                   # NC:744 (debug history: mean |f_orig|)
         svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
         fk = self.hist["fast_keys"]
         for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)

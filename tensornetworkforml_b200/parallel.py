@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-N_EXTRA = 4   # n_correct, sum |y - f|, number of samples, spare
+N_EXTRA = 4   # n_correct, sum |y - f|, number of samples, sum |f| (debug history)
 
 
 def shard_bounds(Ns: int, rank: int, world: int):
