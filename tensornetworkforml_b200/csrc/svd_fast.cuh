@@ -5,11 +5,14 @@
 // same-direction visits, sigma_{m+1} / sigma_m ~ 1e-6).  With V0 = the m dominant short-side singular vectors of the
 // previous visit (rows of the "warm" buffer) the split of the n x n Gram matrix G (n = 128, m = 64) becomes
 //
-//   Y = V0 G                      one subspace-iteration step (error (lambda_{m+1}/lambda_m) tan(angle) ~ 1e-17)
-//   Q = L^-1 Y,  Y Y^T = L L^T    CholeskyQR (Y is nearly orthogonal up to column scaling: cond ~ 1)
+//   Y = V0 G                      one subspace-iteration step (error (lambda_{m+1}/lambda_m) tan(angle) ~ 1e-17); up to
+//                                 four when the residual gate asks for more
+//   Q = D^-1/2 L^-1 Y             CholeskyQR through the LDL^T elimination of Y Y^T, applied to Y at once (blocked,
+//                                 rank-8 DMMA trailing updates; Y is nearly orthogonal up to row scaling: cond ~ 1)
 //   Z = Q G, T = Q Z^T            Rayleigh-Ritz matrix (m x m), residual Z - T Q  -> a-posteriori gate
-//   T = W diag(lam) W^T           two-sided cyclic Jacobi on 64 x 64 in shared memory (ONE CTA, one barrier per
-//                                 rotation set; an eighth of the work of the 128 x 128 problem, no cluster, no L2 trips)
+//   T = W diag(lam) W^T           one-sided cyclic Jacobi on the rows of the 64 x 64 matrix T in ONE CTA (register blocks
+//                                 of 4 + 4 rows per warp, rotation parameters computed once per warp instruction; an
+//                                 eighth of the work of the 128 x 128 problem, no cluster, no L2 round trips)
 //   U_m = W^T Q                   the m dominant singular vectors, lam = sigma^2
 //
 // Everything is verified on the device; when a gate fails (no usable warm basis, no gap at m, kept singular values
