@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
                                                       int m_split, int* __restrict__ split_out,
                                                       long long batch_stride = 0, int hold = 0,
                                                       const double* __restrict__ fastf = nullptr,
-                                                      double* __restrict__ warm_hdr = nullptr) {
+                                                      double* __restrict__ warm_hdr = nullptr, int m_defer = 0,
+                                                      int* __restrict__ defer_sub = nullptr) {
   // hold > 1: launched as ONE cluster of `hold` CTAs of which only rank 0 works; the others wait at the cluster barrier
   // and thereby keep `hold` SMs of one GPC occupied until this kernel ends -- the cluster sweeps that follow on the same
   // stream then find a GPC with enough free SMs although the projection has filled the rest of the GPU meanwhile
@@ -532,7 +533,26 @@ __global__ void __launch_bounds__(NP * 4, 1) k_jacobi(const double* __restrict__
       mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
       mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
-    if (lane == 0) *skip_flag = (mn > 1e-7 * mx) ? 1.0 : 0.0;
+    // Deferred tail on the single-CTA path (m_defer = number of singular triplets the caller keeps), the rule of
+    // k_jacobi_finish: the values below 1e-3 sigma_max form the trailing block (the rows are sorted); when every kept
+    // value sits in the accurate leading block the factors do not need the second pass -- only the reported values of
+    // the discarded tail do, and the tail call (off the critical path) refines those.
+    int cnt = 0;
+    if (m_defer > 0 && defer_sub) {
+      const double thr = (use_chol ? 1e-6 : 1e-12) * mx;
+      for (int r = lane; r < n; r += 32) cnt += nrm2[r] < thr;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) {
+      const bool defer = m_defer > 0 && defer_sub && cnt > 0 && cnt <= 64 && (n - cnt) >= m_defer;
+      skip_flag[0] = (defer || mn > 1e-7 * mx) ? 1.0 : 0.0;
+      if (m_defer > 0 && defer_sub) {
+        skip_flag[1] = defer ? 0.0 : 1.0;
+        defer_sub[0] = defer ? cnt : 0;
+        defer_sub[1] = n - cnt;
+      }
+    }
   }
   if (warm_hdr && tid == 0) { warm_hdr[0] = 1.0; warm_hdr[1] = (double)n; warm_hdr[2] = (double)m_split; }
 }
@@ -1424,19 +1444,22 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
                          int pass_id, double* info, double* skip, const double* lam_prev, JacobiBuffers jb, int* sub,
                          cudaStream_t st, int m_defer = 0, int m_keep = 0, int* split_slot = nullptr,
                          cudaEvent_t gram_done = nullptr, double* warm_hdr = nullptr, bool force_single = false,
-                         const double* fastf = nullptr) {
+                         const double* fastf = nullptr, int* defer_sub = nullptr) {
   const bool cluster = !force_single && (n > 128 || (n > 64 && jacobi_cluster_enabled()));
   if (!cluster) {
     TNML_COUNT(1);
     if (n > 64)
       k_jacobi<128><<<1, 512, 128 * 128 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                   lam_prev, nullptr, nullptr, nullptr, 0, nullptr, 0LL, 0, fastf);
+                                                   lam_prev, nullptr, nullptr, nullptr, 0, nullptr, 0LL, 0, fastf, nullptr,
+                                                   defer_sub ? m_defer : 0, defer_sub);
     else if (n > 32)
       k_jacobi<64><<<1, 256, 64 * 64 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
+                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr, 0LL, 0, nullptr, nullptr,
+                                                defer_sub ? m_defer : 0, defer_sub);
     else
       k_jacobi<32><<<1, 128, 32 * 32 * 8, st>>>(partial, nparts, n, Vt, lam, 40, tol, use_chol, pass_id, info, skip,
-                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr);
+                                                lam_prev, nullptr, nullptr, nullptr, 0, nullptr, 0LL, 0, nullptr, nullptr,
+                                                defer_sub ? m_defer : 0, defer_sub);
     return tnml_launch_status();
   }
   const int* sub2 = (pass_id >= 2) ? sub : nullptr;   // sub-block mode of the second pass
@@ -1475,7 +1498,7 @@ static int launch_jacobi(const double* partial, int nparts, int n, double* Vt, d
         const int* sub_c = sub2;
         cudaError_t ce = cudaLaunchKernelEx(&cfg, k_jacobi<128>, scratch_c, 1, n, Vt, lam, 0, tol, use_chol, pass_id, info,
                                             skip, lam_prev_c, jb.Wg, jb.flags, sub_c, m_keep, split, 0LL, 8,
-                                            (const double*)nullptr, (double*)nullptr);
+                                            (const double*)nullptr, (double*)nullptr, 0, (int*)nullptr);
         if (ce != cudaSuccess) return TNML_CUDA_ERR(ce);
       } else {
         if (gram_done) cudaEventRecord(gram_done, st);
@@ -1609,11 +1632,13 @@ __global__ void __launch_bounds__(256) k_short(const double* __restrict__ Vt1, c
   out[map(s) + (long long)k * kstride] = sqrt(sqrt(lam[k])) * v;
 }
 
+// tail record layout (see svd_tail_record): header, compact Gram matrix, rotation scratch, eigenvalues
+constexpr int TAIL_REC_GRAM = 8, TAIL_REC_VT = 8 + 4096, TAIL_REC_LAM = 8 + 8192, TAIL_REC_DOUBLES = 8 + 8192 + 64;
 struct SvdPlan {
   int R, C, n, Nl, nparts, lc, NP;
   bool rows_short;
   size_t off_partial, off_vt1, off_vt2, off_lam1, off_lam2, off_Y, off_skip, off_Wg, off_nrm, off_flags, off_sub, off_fg,
-      total;
+      off_rec, total;
 };
 
 static SvdPlan svd_plan_rc(int R, int C) {
@@ -1643,6 +1668,8 @@ static SvdPlan svd_plan_rc(int R, int C) {
   p.off_sub = o; o += 2;      // 4 ints: {ns, k0} of the second pass, the two-group split flag, spare
   // warm-started split for n = 256 / 512 (generic form: GEMMs in global memory, see fast_generic): G, six (n/2) x n
   // panels, three (n/2) x (n/2) matrices, eigenvalues, gate scalars, the inner solve's own flags
+  p.off_rec = o;              // scratch tail record (single-CTA deferral without a caller-side record)
+  if (p.n <= 128) o += TAIL_REC_DOUBLES;
   p.off_fg = o;
   if (p.n > 128) o += (size_t)p.n * p.n + 6 * (size_t)(p.n / 2) * p.n + 3 * (size_t)(p.n / 2) * (p.n / 2) + p.n + 32;
   p.total = o;
@@ -1957,6 +1984,9 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
   const bool fastg = fast_hint && warm && refine == 3 && fast_generic_shape(n, m);   // n = 256 / 512: generic form
   const bool cluster = !fast && (n > 128 || (n > 64 && jacobi_cluster_enabled()));
   const int m_defer = (refine == 3 && cluster) ? m : 0;     // refine 3 = refine 1 + deferred tail (svd_tail)
+  // the same on the single-CTA path (n <= 64, or n <= 128 with the cluster kernel switched off), as long as the deferred
+  // block fits a tail record (the path's own fallback behind a fast attempt keeps the plain rule)
+  int* defer_sub = (refine == 3 && !cluster && !fast && n <= 128 && n - m <= 64) ? (int*)(w + p.off_sub) : nullptr;
   if (refine == 3) refine = 1;
   double* skip1 = refine == 1 ? skip : nullptr;
   // refine == 1 on the cluster path: the second pass only decomposes the block of small singular values
@@ -1987,8 +2017,9 @@ static int svd_core(const double* X, SvdPlan p, int m, int refine, double* dst_r
     } else if (skip1) {
       cudaMemsetAsync(skip + 2, 0, sizeof(double), st);   // no fast attempt: the cold kernels must not see a stale flag
     }
-    rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st, m_defer,
-                       m, (int*)(w + p.off_sub) + 2, gram_done, warm_hdr);
+    rc = launch_jacobi(partial, p.nparts, n, vt1, lam1, tol_final, 1, 1, svals + n, skip1, nullptr, jb, sub, st,
+                       defer_sub ? m : m_defer, m, (int*)(w + p.off_sub) + 2, gram_done, warm_hdr, false, nullptr,
+                       defer_sub);
     if (rc == 0 && warm_hdr && !cluster) {            // single-CTA pipeline (n <= 64): the header is written separately
       TNML_COUNT(1);
       k_warm_header<<<1, 32, 0, st>>>(warm_hdr, n, m, nullptr);
@@ -2040,7 +2071,7 @@ static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w,
                     double* warm = nullptr) {
   const int n = p.n, Nl = p.Nl;
   const bool cluster = n > 128 || (n > 64 && jacobi_cluster_enabled());
-  if (!cluster) return TNML_OK;                       // refine 3 never defers on the single-CTA path
+  if (!cluster) return TNML_OK;   // (single-CTA path: only reached when the block is too large for a record: not deferred)
   double *partial = w + p.off_partial, *vt2 = w + p.off_vt2, *lam1 = w + p.off_lam1, *lam2 = w + p.off_lam2,
          *Y = w + p.off_Y, *skip2 = w + p.off_skip + 1;
   JacobiBuffers jb{w + p.off_Wg, w + p.off_nrm, (int*)(w + p.off_flags), Y};
@@ -2081,7 +2112,6 @@ static int svd_tail(const double* X, SvdPlan p, int m, double* svals, double* w,
 // tnml_svd_tail_batch solves all records of a sweep at once, one CTA each, when the history is read.
 // Record (doubles): [0] = {int ns, int k0}, [1] = skip flag, [2] = sweeps used, [3] = n, [8, 8+4096) Gram (ns x ns,
 // compact), [.., +4096) rotation scratch, [.., +64) eigenvalues.
-constexpr int TAIL_REC_GRAM = 8, TAIL_REC_VT = 8 + 4096, TAIL_REC_LAM = 8 + 8192, TAIL_REC_DOUBLES = 8 + 8192 + 64;
 
 __global__ void k_tail_record_hdr(double* __restrict__ rec, const int* __restrict__ sub, const double* __restrict__ skip2,
                                   int n) {
@@ -2211,9 +2241,16 @@ extern "C" int tnml_svd_split_tail_warm(const void* Bnew, void* svals, void* ws,
     const int rc = fast_generic_complement(p, m, (double*)warm, (double*)ws + p.off_skip, (double*)ws, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  if (record && cluster && p.n <= 128 && p.n - m <= 64)      // the deferred block has at most n - m <= 64 rows
+  if (record && p.n <= 128 && p.n - m <= 64)                 // the deferred block has at most n - m <= 64 rows
     return svd_tail_record((const double*)Bnew, p, m, (double*)record, (double*)ws, (cudaStream_t)stream, (double*)warm,
                            fastm);
+  if (!record && !cluster && p.n - m <= 64) {
+    // single-CTA path without a caller-side record: record into the workspace and solve at once
+    double* rec = (double*)ws + p.off_rec;
+    int rc = svd_tail_record((const double*)Bnew, p, m, rec, (double*)ws, (cudaStream_t)stream, (double*)warm, false);
+    if (rc) return rc;
+    return tnml_svd_tail_batch(rec, 1, svals, (int64_t)p.n + 2, dtype, stream);
+  }
   if (record) {                                              // nothing recorded: mark the record as empty
     k_tail_record_hdr_empty<<<1, 32, 0, (cudaStream_t)stream>>>((double*)record);
   }

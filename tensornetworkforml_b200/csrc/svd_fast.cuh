@@ -550,7 +550,6 @@ __global__ void __launch_bounds__(NT, 1) k_fast_split(const double* __restrict__
   double* A1 = fsm + FS_OFF_A1;
   double* A2 = fsm + FS_OFF_A2;
   double* Sm = fsm + FS_OFF_S;
-  double* Wm = fsm + FS_OFF_W;
   double* misc = fsm + FS_OFF_MISC;
   double *dsave = misc, *nrm2 = misc + 64, *red = misc + 384, *lamv = misc + 416, *invn = misc + 480;
   int* ord = reinterpret_cast<int*>(misc + 544);
