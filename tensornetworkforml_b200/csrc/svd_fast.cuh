@@ -158,7 +158,7 @@ __device__ __forceinline__ double fs_rcp(double x) {   // x > 0, normal: MUFU se
 // SAME elimination steps are applied to the rows of Y, so that Out = D^-1/2 L^-1 Y has orthonormal rows.  BLOCKED, 8
 // columns at a time: inside a block eight short steps touch only the 64 x 8 panel of S and the block's eight rows of Y
 // (a few FMAs per thread, one barrier each: the chain load pivot -> reciprocal -> multiplier -> FMA is what bounds a
-// step), then ONE rank-8 trailing update of S and of the remaining rows of Y on the DMMA pipe.  72 barriers, 61 k cycles;
+// step), then ONE rank-8 trailing update of S and of the remaining rows of Y on the DMMA pipe.  72 barriers, 51 k cycles;
 // the un-blocked register-resident form before it took 64 steps of ~1300 cycles (in-order issue of ~190 instructions
 // per warp while the other warps waited at the barrier: 85 k), a right-looking Cholesky + forward substitution 164 k.
 // Returns false (uniformly) when a pivot falls below 1e-10 of the largest diagonal entry (Y was far from orthogonal: no
@@ -177,22 +177,49 @@ __device__ __forceinline__ bool fs_orthonormalize_blocked(double* __restrict__ S
     const int k0 = 8 * kb;
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + j;
+      // every operand of this step is loaded BEFORE the reciprocal of the pivot is needed (fixed thread -> element map,
+      // fully unrolled): the step's chain is max(load, reciprocal) -> multiply -> FMA -> store -> barrier
       const double d = S[k * FS_LDS + k];
+      const int kend = k0 + 8;
+      // Y: thread -> column ycol, rows k + 1 + yr, k + 1 + yr + YS, ... (YS = row groups of the CTA)
+      const int ycol = tid & (FS_N - 1), yr = tid >> 7, YS = (int)blockDim.x >> 7;
+      const double yk = Y[k * FS_LDV + ycol];
+      double yv[4], ym[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + 1 + yr + YS * u;
+        const bool on = u * YS < 7 && kk < kend;
+        yv[u] = on ? Y[kk * FS_LDV + ycol] : 0.0;
+        ym[u] = on ? S[kk * FS_LDS + k] : 0.0;
+      }
+      // panel of S: thread -> row pi, columns k + 1 + pc, k + 1 + pc + PS, ...
+      const int pi = tid & (FS_M - 1), pc = tid >> 6, PS = (int)blockDim.x >> 6;
+      const double sik = S[pi * FS_LDS + k];
+      double pv[2], pm[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = k + 1 + pc + PS * u;
+        const bool on = c < kend && pi >= c;
+        pv[u] = on ? S[pi * FS_LDS + c] : 0.0;
+        pm[u] = on ? S[c * FS_LDS + k] : 0.0;
+      }
       if (!(d > floor_)) return false;                                   // uniform
       const double rcp = fs_rcp(d);
       if (tid == 0) dsave[k] = d;
       // multipliers of this column (also kept for the trailing update)
-      if (tid < FS_M && tid > k) Lp[tid * FS_LDP + j] = S[tid * FS_LDS + k] * rcp;
-      // panel: S[i][c] -= (S[i][k] / d) S[c][k] for k < c < k0 + 8, i >= c
-      const int nc = 7 - j;                                              // remaining columns of the block
-      for (int e = tid; e < nc * FS_M; e += (int)blockDim.x) {
-        const int c = k + 1 + e / FS_M, i = e % FS_M;
-        if (i >= c) S[i * FS_LDS + c] = fma(-S[i * FS_LDS + k] * rcp, S[c * FS_LDS + k], S[i * FS_LDS + c]);
-      }
+      if (tid < FS_M && tid > k) Lp[tid * FS_LDP + j] = sik * rcp;
       // the block's remaining rows of Y: Y[k'] -= (S[k'][k] / d) Y[k]
-      for (int e = tid; e < nc * FS_N; e += (int)blockDim.x) {
-        const int kk = k + 1 + e / FS_N, col = e % FS_N;
-        Y[kk * FS_LDV + col] = fma(-S[kk * FS_LDS + k] * rcp, Y[k * FS_LDV + col], Y[kk * FS_LDV + col]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + 1 + yr + YS * u;
+        if (u * YS < 7 && kk < kend) Y[kk * FS_LDV + ycol] = fma(-ym[u] * rcp, yk, yv[u]);
+      }
+      // panel: S[i][c] -= (S[i][k] / d) S[c][k] for k < c < k0 + 8, i >= c
+      const double li = sik * rcp;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = k + 1 + pc + PS * u;
+        if (c < kend && pi >= c) S[pi * FS_LDS + c] = fma(-li, pm[u], pv[u]);
       }
       __syncthreads();
     }
