@@ -219,14 +219,15 @@ class Network():
         if data.ndim != 3 or data.shape[1] != self.N or data.shape[2] != 2:
             return None
         import torch
-        cache = self.__dict__.setdefault("_resident_cache", {})
-        hit = cache.get(id(ds))
+        cache = self.__dict__.setdefault("_resident_cache", {})   # at most two datasets (train + validation), LRU
+        hit = cache.pop(id(ds), None)
         if hit is None or hit[0] is not ds:
             dev = self._engine().device
             hit = (ds, torch.from_numpy(np.ascontiguousarray(data, dtype=np.float64)).to(dev),
                    torch.from_numpy(np.ascontiguousarray(np.asarray(label), dtype=np.int32)).to(dev))
-            cache.clear()
-            cache[id(ds)] = hit
+            while len(cache) >= 2:
+                cache.pop(next(iter(cache)))
+        cache[id(ds)] = hit
         return hit[1], hit[2]
 
     @staticmethod
