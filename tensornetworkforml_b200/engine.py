@@ -694,6 +694,7 @@ class SweepEngine:
                 new_p = new_p.view(-1, m)[:, :m_keep].contiguous().view(-1)
                 new_q = new_q.view(m, -1)[:m_keep].contiguous().view(-1)
                 m = m_keep
+                self._ald_for = None      # the metric sums computed ahead sit where the cap's bond tensor would end
         self.sites[p], self.sites[q] = new_p, new_q
         self.bonds[q] = m
         self.l_pos += -1 if left_dir else 1                                                 # NC:568-571

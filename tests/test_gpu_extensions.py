@@ -256,7 +256,10 @@ def test_adaptive_truncation_follows_the_oracle(tn, threshold, min_bond):
         left = orc.l_pos == S - 1
         n0 = len(orc.hist)
         fo = orc.sweep(y, fo, 0.02, 0.01, True, left)
-        f = net.sweep(X, y, f, 0.02, 0.01, L2_flag=True, left_dir=left)
+        vh = [[], []]
+        f = net.sweep(X, y, f, 0.02, 0.01, L2_flag=True, left_dir=left, var_hist=vh)
+        assert np.abs(np.array(vh[0]) - [r["acc"] for r in orc.hist[n0:]]).max() < 1e-12
+        assert np.abs(np.array(vh[1]) - [r["mae"] for r in orc.hist[n0:]]).max() < TOL
         assert net._eng.bond_dims() == orc.bond_dims(), "sweep %d" % sw
         assert G.rel(f.elem.T, fo) < TOL
         assert net.last_history["m"] == [r["m"] for r in orc.hist[n0:]]
