@@ -203,6 +203,9 @@ int tnml_svd_split_tail(const void* Bnew, void* svals, void* ws, void* record, i
  * on the 64 x 64 projected Gram matrix (two-sided Jacobi in one CTA), a-posteriori residual / gap / conditioning
  * gates on the device -- and runs the ordinary pipeline (single-CTA form) only when a gate fails.  Results agree with
  * the cold split to rounding.  fast = 0 or warm = NULL: exactly tnml_svd_split_ev (plus the rotation left in `warm`).
+ * With fast != 0 svals must hold min(R, C) + 14 values: svals[n] >= 100 marks a split that took the deflation path
+ * (100 + Jacobi sweeps), svals[n+2] / svals[n+3] the refusal code and the deciding ratio otherwise, svals[n+4 .. n+13]
+ * the phase clocks of the single-CTA kernel (diagnostics).
  * The tail call must receive the same warm / fast arguments. */
 int64_t tnml_svd_warm_bytes(int32_t Dl, int32_t Dr, int32_t L, int32_t left_dir);
 int tnml_svd_split_warm(const void* Bnew, void* site_p, void* site_q, void* svals, void* ws, void* warm, int32_t Dl,
