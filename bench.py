@@ -403,7 +403,15 @@ def main():
         line["cpu_baseline"] = dict(value=1.0 / per, unit="bond-updates/s", cores=host_threads(), kind="port",
                                     sample="3 interior bond updates (D=%d both sides, L=%d) at the full Ns=%d with the "
                                            "NumPy/OpenBLAS oracle port of sweep_step (1 warm-up update)" % (D, L, Ns),
-                                    s_per_sweep_extrapolated=per * (S - 1))
+                                    s_per_sweep_extrapolated=per * (S - 1),
+                                    verbatim_reference=dict(
+                                        note="the reference itself (only tensor_svd's m replaced) cannot run this shape "
+                                             "(78 GB intermediate in update_B) and does not exist on the GPU box; measured "
+                                             "in the build container by tools/ref_verbatim_point.py, BASELINE.md section 2",
+                                        measured_s_per_bond_update={"Ns=64": 0.54, "Ns=128": 0.75, "Ns=256": 1.58},
+                                        config="S=16, D=64, L=10, L2_flag=False, interior bonds",
+                                        extrapolated_s_per_bond_update_at_Ns_60000=324.0,
+                                        l2_term_extra_s_per_bond_update={"S=16": 4.7, "S=196 (O(S))": 57.0}))
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -55,6 +55,21 @@ def choose_m(rule, max_bond, left_dir, l_pos, S, Dl, R, C):
     return nS
 
 
+def warm_feedback(fails, waits, key, accepted):
+    """Host side of the warm-started split's backoff (SweepEngine.history -> split_phase).  ``accepted``: the device-side
+    gates took the attempt of bond ``key``.  In the first sweeps of a training run the tensors still change a lot between
+    visits (the basis of the previous visit is then a poor start: the subspace steps do not converge, or the
+    orthonormalisation does not): a refused bond tries again at its next visit.  A second refusal in a row (no gap at m --
+    typical for the bonds next to the chain ends) sends it back to the cold pipeline for two visits, then it tries again;
+    an accepted attempt clears the count."""
+    if accepted:
+        fails.pop(key, None)
+        return
+    n = fails.get(key, 0) + 1
+    fails[key] = n
+    waits[key] = 0 if n < 2 else 2
+
+
 class _Timed:
     """Optional CUDA-event bracket around one C-ABI call (bench.py's live per-kernel timing)."""
 
@@ -734,19 +749,8 @@ class SweepEngine:
         svals = [sv[i, :self.hist["nsv"][i]] for i in range(n)]
         fk = self.hist["fast_keys"]
         for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)
-            if ent is None:
-                continue
-            nsv_i = self.hist["nsv"][ent[0]]
-            if sv[ent[0], nsv_i] >= 100:
-                self._warm_fail.pop(ent[1], None)
-                continue
-            # refused.  In the first sweeps of a training run the tensors still change a lot between visits (the basis
-            # of the previous visit is then a poor start: the subspace steps do not converge, or the orthonormalisation
-            # does not): try again at the next visit.  A second refusal in a row (no gap at m -- typical for the bonds
-            # next to the chain ends): sit out two visits, then try again.
-            fails = self._warm_fail.get(ent[1], 0) + 1
-            self._warm_fail[ent[1]] = fails
-            self._warm_wait[ent[1]] = 0 if fails < 2 else 2
+            if ent is not None:
+                warm_feedback(self._warm_fail, self._warm_wait, ent[1], sv[ent[0], self.hist["nsv"][ent[0]]] >= 100)
         self.hist["fast_seen"] = len(fk)
         return dict(acc=acc, mae=mae, absf=absf, stats=stats, svals=svals, m=list(self.hist["m"]))
 

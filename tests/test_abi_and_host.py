@@ -193,3 +193,25 @@ def test_index_batches_reproduce_the_loader_and_its_rng_consumption():
         ld = loaders()[k]
         mine = [[int(i) for i in b] for b in Network._index_batches(ld)]
         assert mine == real and torch.equal(torch.get_rng_state(), st_real), "loader %d" % k
+
+
+def test_warm_split_backoff_policy():
+    """Host logic of the warm-started split (engine.warm_feedback + the wait counter consumed in split_phase): one free
+    retry after a refusal, two visits on the cold pipeline after a second refusal in a row, reset by an accepted attempt."""
+    from tensornetworkforml_b200.engine import warm_feedback
+    fails, waits, key = {}, {}, (5, 0, 64, 64)
+
+    def visit(outcome):
+        """-> whether the visit attempts the fast path; outcome = what the gates say if it does"""
+        if waits.get(key, 0) > 0:
+            waits[key] -= 1
+            return False
+        warm_feedback(fails, waits, key, outcome)
+        return True
+
+    assert visit(False) and visit(False)              # refused, free retry, refused again
+    assert not visit(True) and not visit(True)        # two visits sit out
+    assert visit(False)                               # tried again, third refusal in a row: back off again
+    assert not visit(True) and not visit(True)
+    assert visit(True) and fails == {}                # accepted: the count is cleared
+    assert visit(False) and visit(True) and visit(True)   # a single refusal only costs the attempt
