@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--ns", type=int, default=CFG["Ns"], help="total samples (default: the BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the API arm (bond-dimension sweeps: device numbers only)")
+    ap.add_argument("--no-kernel-pass", action="store_true",
+                    help="skip the second, event-bracketed pass (no per-kernel table and no roofline object: A/B runs only)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
                     help="f64 = the parity path (default, the BASELINE metric); f32 = FP32 storage / TF32 tcgen05 variant")
     ap.add_argument("--D", type=int, default=CFG["D"], help="bond dimension (other BASELINE.json configs)")
@@ -282,7 +284,7 @@ def main():
     eng.timers = {}
     t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0e.record()
-    for _ in range(args.steps):
+    for _ in range(0 if args.no_kernel_pass else args.steps):
         device_step()
     t1e.record()
     barrier()
@@ -342,6 +344,8 @@ def main():
         peak = (json.load(open(mp))["bf16_tflops"] / 2) if os.path.exists(mp) else 1100.0
         peak_src = "half of the measured bf16 burst peak in MEASURED_PEAKS.json (TF32 = bf16 / 2 on tcgen05); not measured directly"
         kname, traffic = "k_grad_tc (tcgen05 kind::tf32)", None
+    if args.no_kernel_pass:
+        kern[top] = dict(calls=0, ms_total=0.0, share=0.0, tflops=0.0, avg_ms=0.0)
     roofline = dict(kernel=kname, bound="tensor", achieved=kern[top]["tflops"], peak=peak, unit="TFLOP/s",
                     frac=kern[top]["tflops"] / peak, traffic=traffic, peak_source=peak_src,
                     flops_per_launch="8*Ns*L*Dl*Dr per launch (2 flops x Ns x (2 Dl) x (2 L Dr)), summed over the "

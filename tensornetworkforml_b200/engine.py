@@ -55,19 +55,30 @@ def choose_m(rule, max_bond, left_dir, l_pos, S, Dl, R, C):
     return nS
 
 
-def warm_feedback(fails, waits, key, accepted):
+def warm_feedback(fails, waits, key, accepted, single_cta=False):
     """Host side of the warm-started split's backoff (SweepEngine.history -> split_phase).  ``accepted``: the device-side
     gates took the attempt of bond ``key``.  In the first sweeps of a training run the tensors still change a lot between
     visits (the basis of the previous visit is then a poor start: the subspace steps do not converge, or the
     orthonormalisation does not): a refused bond tries again at its next visit.  A second refusal in a row (no gap at m --
-    typical for the bonds next to the chain ends) sends it back to the cold pipeline for two visits, then it tries again;
-    an accepted attempt clears the count."""
+    typical for the bonds next to the chain ends, and for more bonds the longer the training runs) sends it back to the
+    cold pipeline, then it tries again; an accepted attempt clears the count.
+    How long it sits out is a matter of what the two outcomes cost.  ``single_cta`` (n = 128, k_fast_split): a refused
+    attempt is followed by the single-CTA form of the cold pipeline (~2.5 ms more than an accepted one) while a visit on
+    the cold cluster pipeline costs 0.1 - 0.3 ms more, so a bond that keeps refusing backs off exponentially: 4, 8, 16
+    visits (with 2 every time, 20 sweeps into the bench run a third of those bonds refused in every sweep: 324 -> 345 ms).
+    Generic form (n = 256 / 512): the cold pipeline is 2.5x slower than the warm-started one, sitting out is nearly as
+    expensive as a refusal: two visits, as before."""
     if accepted:
         fails.pop(key, None)
         return
     n = fails.get(key, 0) + 1
     fails[key] = n
-    waits[key] = 0 if n < 2 else 2
+    if n < 2:
+        waits[key] = 0
+    elif not single_cta:
+        waits[key] = 2
+    else:
+        waits[key] = min(4 << (n - 2), 16)
 
 
 class _Timed:
@@ -750,7 +761,8 @@ class SweepEngine:
         fk = self.hist["fast_keys"]
         for ent in fk[self.hist["fast_seen"]:]:       # feedback for the next visits of each bond (see _warm_wait)
             if ent is not None:
-                warm_feedback(self._warm_fail, self._warm_wait, ent[1], sv[ent[0], self.hist["nsv"][ent[0]]] >= 100)
+                nshort = self.hist["nsv"][ent[0]]
+                warm_feedback(self._warm_fail, self._warm_wait, ent[1], sv[ent[0], nshort] >= 100, single_cta=nshort == 128)
         self.hist["fast_seen"] = len(fk)
         return dict(acc=acc, mae=mae, absf=absf, stats=stats, svals=svals, m=list(self.hist["m"]))
 

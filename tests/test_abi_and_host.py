@@ -197,21 +197,31 @@ def test_index_batches_reproduce_the_loader_and_its_rng_consumption():
 
 def test_warm_split_backoff_policy():
     """Host logic of the warm-started split (engine.warm_feedback + the wait counter consumed in split_phase): one free
-    retry after a refusal, two visits on the cold pipeline after a second refusal in a row, reset by an accepted attempt."""
+    retry after a refusal; after a second refusal in a row two visits on the cold pipeline (generic form) or 4, 8, 16, 16
+    ... visits (single-CTA form, where a refusal is ten times as expensive as sitting out); reset by an accepted attempt."""
     from tensornetworkforml_b200.engine import warm_feedback
-    fails, waits, key = {}, {}, (5, 0, 64, 64)
 
-    def visit(outcome):
-        """-> whether the visit attempts the fast path; outcome = what the gates say if it does"""
-        if waits.get(key, 0) > 0:
-            waits[key] -= 1
-            return False
-        warm_feedback(fails, waits, key, outcome)
-        return True
+    def run(single_cta, outcomes):
+        """-> per visit whether it attempts the fast path; outcomes = what the gates say at each attempt"""
+        fails, waits, key, tried = {}, {}, (5, 0, 64, 64), []
+        outcomes = iter(outcomes)
+        while True:
+            if waits.get(key, 0) > 0:
+                waits[key] -= 1
+                tried.append(False)
+                continue
+            try:
+                warm_feedback(fails, waits, key, next(outcomes), single_cta=single_cta)
+            except StopIteration:
+                return tried, fails
+            tried.append(True)
 
-    assert visit(False) and visit(False)              # refused, free retry, refused again
-    assert not visit(True) and not visit(True)        # two visits sit out
-    assert visit(False)                               # tried again, third refusal in a row: back off again
-    assert not visit(True) and not visit(True)
-    assert visit(True) and fails == {}                # accepted: the count is cleared
-    assert visit(False) and visit(True) and visit(True)   # a single refusal only costs the attempt
+    T, F = True, False
+    tried, fails = run(False, [F, F, F, T, F, T, T])
+    #               refused, free retry refused, 2 out, refused, 2 out, accepted, single refusal, accepted twice
+    assert tried == [T, T, F, F, T, F, F, T, T, T, T] and fails == {}
+    tried, _ = run(True, [F, F, F, F, F, F])
+    gaps = [len(g) for g in "".join("x" if t else "." for t in tried).split("x")[1:]]
+    assert gaps == [0, 4, 8, 16, 16, 16]              # free retry, then exponential, capped
+    tried, fails = run(True, [F, F, T, F, F])         # an accepted attempt starts the count again
+    assert tried == [T, T] + [F] * 4 + [T, T, T] + [F] * 4 and fails[(5, 0, 64, 64)] == 2
