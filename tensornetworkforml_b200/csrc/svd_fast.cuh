@@ -687,7 +687,8 @@ __global__ void __launch_bounds__(NT, 1) k_fast_split(const double* __restrict__
   }
   __syncthreads();
   const double lam1 = lamv[ord[0]], lamm = lamv[ord[FS_M - 1]];
-  const double tau = misc[480] - trT;                  // eigenvalue mass outside the subspace (>= lambda_{m+1})
+  const double tau = misc[576] - trT;                  // trace(G) (written above) - trace(T): eigenvalue mass outside
+                                                       // the subspace (>= lambda_{m+1})
   // gates: residual against the TRUE lambda_m; the subspace is the dominant one (every outside eigenvalue below
   // lambda_m); every kept singular value in the range a single Gram pass resolves (sigma >= 1e-3 sigma_max)
   ok = lamm > 0.0 && resid2 <= 1e-24 * lamm * lamm && tau <= 0.25 * lamm && lamm >= 1e-6 * lam1 && sweeps < 30;

@@ -126,3 +126,28 @@ def test_gates_refuse_what_the_path_cannot_deliver():
     assert fast_split(As @ As.T, Us, m)[0] is None
     Ar = A[:, :40] @ rng.standard_normal((40, 1280))                          # rank 40 < m: CholeskyQR must break down
     assert fast_split(Ar @ Ar.T, U0, m)[0] is None
+
+
+def test_dominance_gate_refuses_an_invariant_subspace_that_is_not_the_dominant_one():
+    """What tr G - tr T <= 0.25 lambda_m is there for: a start basis that is EXACTLY invariant but misses one of the m
+    dominant directions (here eigenvector 64 replaced by eigenvector 65) stays invariant under the subspace steps, so the
+    residual gate passes, and its smallest Ritz value (0.1 lambda_1) passes the range gate -- only the eigenvalue mass
+    left outside the subspace (lambda_64 = 0.5) gives it away.  (The device kernel read tr G from the wrong shared-memory
+    slot until the end of round 2, which made this gate inert for matrices of order-one scale)"""
+    rng = np.random.default_rng(3)
+    n, m = 128, 64
+    W, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([np.linspace(1.0, 0.5, m), [0.1], 1e-12 * np.ones(n - m - 1)])
+    G = (W * lam) @ W.T
+    G = 0.5 * (G + G.T)
+    dominant = W[:, :m].T
+    U, lam_out, info = fast_split(G, dominant, m)
+    assert U is not None and np.abs(np.sort(lam_out)[::-1] - lam[:m]).max() < 1e-13, info
+    swapped = np.vstack([W[:, :m - 1].T, W[:, m:m + 1].T])
+    Q = ldl_orthonormalize(swapped @ G)                      # one subspace step: still invariant, residual at rounding
+    Z = Q @ G
+    T = Q @ Z.T
+    assert np.sqrt(((Z - T @ Q) ** 2).sum()) < 1e-12 * np.linalg.eigvalsh(0.5 * (T + T.T)).min()
+    assert np.trace(G) - np.trace(T) > 0.25 * 0.1
+    assert fast_split(G, swapped, m) == (None, None, "gates")
+
