@@ -7,7 +7,9 @@ side of 2D whose bond was split before in the same direction, runs the NumPy res
 policy would have done (the warm buffer holds the previous visit's basis after either pipeline, so the outcome of an
 attempt does not depend on earlier attempts).  One row per (sweep, bond, direction):
 
-    sweep p dir visit code steps tau/lam_m lam_{m+1}/lam_m lam_m/lam_1 sin(theta) resid/lam_m
+    sweep p dir visit code steps tau/lam_m lam_{m+1}/lam_m lam_m/lam_1 sin(theta) resid/lam_m jacobi_sweeps
+
+(jacobi_sweeps: sweeps of the restated one-sided Jacobi on T with single-precision rotation parameters, JACOBI=1 only.)
 
 code: 0 accepted | 2 CholeskyQR breakdown | 3 residual after the subspace steps | 4.1 residual against the true lam_m |
 4.2 tau > 0.25 lam_m (no gap: the subspace is not the dominant one) | 4.3 lam_m < 1e-6 lam_1.
@@ -23,13 +25,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import mps_oracle as O                                   # noqa: E402
 import tensornetworkforml_b200.data_generator as gen                 # noqa: E402
-from tests.test_fast_split_algorithm import ldl_orthonormalize       # noqa: E402
+from tests.test_fast_split_algorithm import jacobi_rows, ldl_orthonormalize       # noqa: E402
 
 S, L, D = int(os.environ.get("S", 196)), 10, int(os.environ.get("D", 64))
 Ns = int(os.environ.get("NS", 60000))
 NSWEEP = int(os.environ.get("NSWEEP", 25))
 OUT = os.environ.get("OUT", "/tmp/refusal_table.npy")
+JACOBI = os.environ.get("JACOBI", "0") != "0"        # also run the restated single-precision-parameter Jacobi on T
 lr, wd = 1e-4, 1e-3
+LAST = dict(sweeps=np.nan)
 
 
 def attempt(G, V0, m):
@@ -55,6 +59,8 @@ def attempt(G, V0, m):
     if not ok:
         return 3.0, it + 1, (np.sqrt(resid2) / mind if mind > 0 else np.inf)
     lam = np.sort(np.linalg.eigvalsh(T))[::-1]
+    if JACOBI:
+        LAST["sweeps"] = jacobi_rows(T, max_sweeps=60)[1]
     tau = np.trace(G) - np.trace(T)
     rr = np.sqrt(resid2) / lam[-1]
     if not resid2 <= 1e-24 * lam[-1] ** 2:
@@ -91,11 +97,12 @@ def main():
             v = visits[key] = visits.get(key, 0) + 1
             if key in basis:
                 V0 = basis[key]
+                LAST["sweeps"] = np.nan
                 code, steps, rr = attempt(G, V0, m)
                 # sine of the largest principal angle between the old basis and the new dominant subspace
                 sin_t = np.linalg.norm(Vec[:, m:].T @ V0.T, 2)
                 rows.append((cur["sweep"], p, int(left_dir), v, code, steps, w[m:].sum() / w[m - 1], w[m] / w[m - 1],
-                             w[m - 1] / w[0], sin_t, rr))
+                             w[m - 1] / w[0], sin_t, rr, LAST["sweeps"]))
             basis[key] = np.ascontiguousarray(Vec[:, :m].T)
         return orig(B, left_dir, m)
 
