@@ -210,6 +210,8 @@ class SweepEngine:
         caller must not modify X while a load_input(X) is in flight."""
         if not (isinstance(X, np.ndarray) and X.dtype == np.float64 and X.flags["C_CONTIGUOUS"]):
             raise ValueError("register_input needs a C-contiguous float64 ndarray")
+        # registering may evict (cudaHostUnregister) the oldest registration: no copy out of it may still be in flight
+        torch.cuda.synchronize(self.device)
         return _lib.register_host_array(X)
 
     def _side_stream(self):
