@@ -225,3 +225,34 @@ def test_warm_split_backoff_policy():
     assert gaps == [0, 4, 8, 16, 16, 16]              # free retry, then exponential, capped
     tried, fails = run(True, [F, F, T, F, F])         # an accepted attempt starts the count again
     assert tried == [T, T] + [F] * 4 + [T, T, T] + [F] * 4 and fails[(5, 0, 64, 64)] == 2
+
+
+def test_truncation_rule_of_the_engine_equals_the_oracle():
+    """engine.choose_m (host logic in front of tnml_svd_split) against the oracle's restatement of NC:898-910 /
+    NC:933-945 for every label position, direction and shape class -- including WHERE each of them raises (the
+    reference's np.dot failures for L > 2)."""
+    from tensornetworkforml_b200.engine import choose_m as mine
+    from oracle.mps_oracle import choose_m as theirs
+    S = 7
+
+    def outcome(fn, *a):
+        try:
+            return ("ok", fn(*a))
+        except ValueError as e:
+            return ("raises", str(e))
+
+    n = 0
+    for rule, max_bond in (("reference", None), ("fixed", 3), ("fixed", 6), ("fixed", 64)):
+        for left_dir in (False, True):
+            for l_pos in range(S):
+                for Dl in (1, 2, 3, 5):
+                    for Dr in (1, 2, 4):
+                        for L in (2, 3, 10):
+                            R, C = (2 * Dl, 2 * L * Dr) if not left_dir else (2 * Dl * L, 2 * Dr)
+                            a = outcome(mine, rule, max_bond, left_dir, l_pos, S, Dl, R, C)
+                            b = outcome(theirs, rule, left_dir, l_pos, S, Dl, min(R, C), R, C, max_bond)
+                            assert a == b, (rule, max_bond, left_dir, l_pos, Dl, Dr, L, a, b)
+                            n += 1
+    assert n == 4 * 2 * S * 4 * 3 * 3
+    # 'adaptive' asks the split for the cap; the data-dependent cut follows it (engine.split_phase)
+    assert mine("adaptive", 6, False, 2, S, 4, 8, 80) == mine("fixed", 6, False, 2, S, 4, 8, 80) == 6
