@@ -256,3 +256,43 @@ def test_truncation_rule_of_the_engine_equals_the_oracle():
     assert n == 4 * 2 * S * 4 * 3 * 3
     # 'adaptive' asks the split for the cap; the data-dependent cut follows it (engine.split_phase)
     assert mine("adaptive", 6, False, 2, S, 4, 8, 80) == mine("fixed", 6, False, 2, S, 4, 8, 80) == 6
+
+
+def test_site_and_bond_layout_conversions_round_trip():
+    """Host layout glue between the reference's named-axis Tensors and the canonical device layouts (pure NumPy, no
+    device): a site Tensor in ANY axis order maps to (Dl,2,[L,]Dr) and back, the chain ends lose / regain their dummy
+    bond, and a bond Tensor B (NC:484) in any axis order maps to (Dl,2,L,2,Dr) and back into the caller's axis order."""
+    import contextlib
+    import io
+    import itertools
+    from tensornetworkforml_b200 import Network_class as NCm
+    from tensornetworkforml_b200.Tensor_class import Tensor
+    rng = np.random.default_rng(5)
+    S, Dl, Dr, L = 6, 3, 4, 5
+    for p, is_label in itertools.product((0, 2, S - 1), (False, True)):
+        shape = (1 if p == 0 else Dl, 2) + ((L,) if is_label else ()) + (1 if p == S - 1 else Dr,)
+        A = rng.standard_normal(shape)
+        T = NCm._canonical_to_named(A, p, S, is_label)
+        want = ([] if p == 0 else ["left"]) + ["d%d" % p] + (["l"] if is_label else []) + ([] if p == S - 1 else ["right"])
+        want_shape = shape[1 if p == 0 else 0:len(shape) - (1 if p == S - 1 else 0)]     # dummy edge bonds dropped
+        assert [str(n) for n in T.axes_names] == want and T.elem.shape == want_shape
+        for perm in itertools.permutations(range(T.elem.ndim)):
+            Tp = Tensor(elem=np.transpose(T.elem, perm), axes_names=[want[i] for i in perm])
+            assert np.array_equal(NCm._named_to_canonical(Tp, p), A)
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = NCm.Network(N=S, M=3, L=L)              # no calibration: nothing touches the device
+    for p in (0, 2, S - 2):
+        names = net._bond_names(p)
+        shape = [1 if p == 0 else Dl, 2, L, 2, 1 if p == S - 2 else Dr]
+        Bc = rng.standard_normal(shape)
+        keep = [i for i, nm in enumerate(names) if not ((nm == "left" and p == 0) or (nm == "right" and p == S - 2))]
+        base = Bc.reshape([shape[i] for i in keep])
+        for perm in itertools.permutations(range(len(keep))):
+            B = Tensor(elem=np.transpose(base, perm), axes_names=[names[keep[i]] for i in perm])
+            can = net._bond_to_canonical(B, p)
+            assert can.shape == tuple(shape) and np.array_equal(can, Bc)
+            back = net._bond_from_canonical(can * 2.0, B, p)
+            assert [str(n) for n in back.axes_names] == [str(n) for n in B.axes_names]
+            assert np.array_equal(back.elem, 2.0 * B.elem)
+    with pytest.raises(AssertionError):
+        net._bond_to_canonical(Tensor(elem=np.zeros((2, 2)), axes_names=["d1", "bogus"]), 1)
