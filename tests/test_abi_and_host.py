@@ -296,3 +296,35 @@ def test_site_and_bond_layout_conversions_round_trip():
             assert np.array_equal(back.elem, 2.0 * B.elem)
     with pytest.raises(AssertionError):
         net._bond_to_canonical(Tensor(elem=np.zeros((2, 2)), axes_names=["d1", "bogus"]), 1)
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_lines():
+    """bench.py's `clocks` block (median SM clock under load, max clock, throttle reasons seen DURING the timed region) from
+    the CSV lines `nvidia-smi --query-gpu=... -lms 100` writes; without nvidia-smi the block is empty, not an error."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.ClockSampler(None).stop() == dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    smp = bench.ClockSampler(None)
+    smp.proc, smp.fh = _Proc(), open(smp.path, "w")
+    smp.fh.write("0, 1965, 1965, 540.1, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active\n"
+                 "0, 1950, 1965, 990.0, 0x0000000000000004, Not Active, Not Active, Not Active, Active\n"
+                 "0, 1935, 1965, 995.2, 0x0000000000000004, Not Active, Not Active, Not Active, Active\n"
+                 "0, [N/A], 1965, 1.0, 0x0, Not Active, Not Active, Not Active, Not Active\n"
+                 "garbage line\n")
+    smp.fh.flush()
+    out = smp.stop()
+    assert out == dict(sm_mhz=1950.0, sm_max_mhz=1965.0, reasons=["sw_power_cap"], samples=3)
+    assert not os.path.exists(smp.path)
+    cfg = bench.workload_config(196, 10, 64, 60000, "f64")
+    assert cfg["workload"].startswith("config3:") and (cfg["S"], cfg["L"], cfg["D"], cfg["Ns"]) == (196, 10, 64, 60000)
+    assert bench.workload_config(784, 10, 128, 60000, "f64")["workload"].startswith("variant of config3: 28x28")
