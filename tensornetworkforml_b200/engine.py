@@ -81,6 +81,20 @@ def warm_feedback(fails, waits, key, accepted, single_cta=False):
         waits[key] = min(4 << (n - 2), 16)
 
 
+def kept_ratio(svals_row, nshort):
+    """(sigma_m / sigma_1)^2 of a recorded split with short side ``nshort`` = 2 m: how far the KEPT singular values of
+    that bond are graded (nan when the record is incomplete).  The residual gate of the warm-started split (1e-12
+    lambda_m) sits at the floor of a Gram-based pass, ~10 eps lambda_1, once this ratio falls below ~0.1: such bonds --
+    the ones next to the chain ends -- flip between accepted and refused (tools/refusal_study.py)."""
+    m = nshort // 2
+    if m < 1 or len(svals_row) < m:
+        return float("nan")
+    s1, sm = float(svals_row[0]), float(svals_row[m - 1])
+    if not (np.isfinite(s1) and np.isfinite(sm) and s1 > 0.0):
+        return float("nan")
+    return (sm / s1) ** 2
+
+
 class _Timed:
     """Optional CUDA-event bracket around one C-ABI call (bench.py's live per-kernel timing)."""
 
@@ -177,6 +191,11 @@ class SweepEngine:
         # for the next two visits.
         self._warm_wait = {}
         self._warm_fail = {}
+        # opt-in (TNML_FAST_MIN_RATIO, e.g. 0.1; default 0 = off, not yet measured on hardware): a bond whose kept singular
+        # values were graded below this ratio at its previous visit (kept_ratio) does not attempt the single-CTA fast
+        # split at all -- its residual gate is marginal there and every refusal costs 2.5 - 4 ms
+        self.warm_min_ratio = float(os.environ.get("TNML_FAST_MIN_RATIO", "0"))
+        self._warm_ratio = {}
         # Beside the single-CTA fast split the projection leaves two SMs free when it is the longer of the two (large
         # per-GPU batches: the split's small multi-CTA kernels then queue for those two SMs, which does not matter), and
         # sixteen when the split is the critical path (small per-GPU batches, i.e. many GPUs)
@@ -266,7 +285,7 @@ class SweepEngine:
         self.l_pos = int(l_pos)
         self.label_layout = "R"
         self._warm = {}               # new weights: the rotations of earlier visits say nothing about them
-        self._warm_wait, self._warm_fail = {}, {}
+        self._warm_wait, self._warm_fail, self._warm_ratio = {}, {}, {}
         for p, A in enumerate(host_sites):
             A = np.ascontiguousarray(A, dtype=np.float64)
             if p == self.l_pos:
@@ -481,7 +500,7 @@ class SweepEngine:
                          metrics=torch.zeros((nsteps, 4), dtype=torch.float64, device=self.device),
                          stats=torch.zeros((nsteps, 8), dtype=torch.float64, device=self.device),
                          svals=torch.full((nsteps, nmax), float("nan"), dtype=torch.float64, device=self.device),
-                         nsv=[], m=[], n=0, fast_keys=[], fast_seen=0)
+                         nsv=[], m=[], n=0, fast_keys=[], fast_seen=0, warm_keys=[], warm_seen=0)
         self.hist["tail_recs"][:, 1] = 1.0            # "nothing recorded" until a tail call writes the header
         self._st = None
 
@@ -647,6 +666,10 @@ class SweepEngine:
                 self._warm_wait[key] -= 1
             else:
                 fast = 1
+            if self.warm_min_ratio > 0.0:
+                if fast and nshort == 128 and self._warm_ratio.get(key, 1.0) < self.warm_min_ratio:
+                    fast = 0                            # graded at the previous visit: cold pipeline, no attempt
+                self.hist["warm_keys"].append((step, key))
             self.hist["fast_keys"].append((step, key) if fast else None)
         with _Timed(self, "svd_split", 0.0, side):
             call("tnml_svd_split_warm", _ptr(Bn), _ptr(new_p), _ptr(new_q), sv_ptr, _ptr(ws_svd), _ptr(warm), Dl, Dr, L,
@@ -766,6 +789,12 @@ class SweepEngine:
                 nshort = self.hist["nsv"][ent[0]]
                 warm_feedback(self._warm_fail, self._warm_wait, ent[1], sv[ent[0], nshort] >= 100, single_cta=nshort == 128)
         self.hist["fast_seen"] = len(fk)
+        wk = self.hist["warm_keys"]                   # (only filled when the opt-in spectrum rule is on)
+        for step_i, key in wk[self.hist["warm_seen"]:]:
+            r = kept_ratio(sv[step_i], self.hist["nsv"][step_i])
+            if r == r:
+                self._warm_ratio[key] = r
+        self.hist["warm_seen"] = len(wk)
         return dict(acc=acc, mae=mae, absf=absf, stats=stats, svals=svals, m=list(self.hist["m"]))
 
     def bond_dims(self):

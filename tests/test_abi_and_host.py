@@ -328,3 +328,15 @@ def test_bench_clock_sampler_parses_nvidia_smi_lines():
     cfg = bench.workload_config(196, 10, 64, 60000, "f64")
     assert cfg["workload"].startswith("config3:") and (cfg["S"], cfg["L"], cfg["D"], cfg["Ns"]) == (196, 10, 64, 60000)
     assert bench.workload_config(784, 10, 128, 60000, "f64")["workload"].startswith("variant of config3: 28x28")
+
+
+def test_kept_ratio_of_a_recorded_split():
+    """engine.kept_ratio: (sigma_m / sigma_1)^2 from a row of the sweep's singular-value record -- what the opt-in rule
+    TNML_FAST_MIN_RATIO compares (a bond graded below it at its previous visit does not attempt the warm-started split)."""
+    from tensornetworkforml_b200.engine import kept_ratio
+    row = np.full(260, np.nan)
+    row[:128] = np.concatenate([np.linspace(2.0, 0.5, 64), 1e-6 * np.ones(64)])
+    assert kept_ratio(row, 128) == pytest.approx((0.5 / 2.0) ** 2)
+    assert np.isnan(kept_ratio(np.full(260, np.nan), 128))              # nothing recorded
+    assert np.isnan(kept_ratio(np.zeros(260), 128))                     # sigma_1 = 0
+    assert np.isnan(kept_ratio(row[:10], 128)) and np.isnan(kept_ratio(row, 0))

@@ -48,6 +48,17 @@ def spectrum(max_tau, max_ratio, inner):
     return decide, f0
 
 
+def graded(min_ratio, inner):
+    """engine.SweepEngine's opt-in rule (TNML_FAST_MIN_RATIO): no attempt while the kept singular values of the bond were
+    graded below (sigma_m / sigma_1)^2 = min_ratio at its previous visit; otherwise like `inner`."""
+    d0, f0 = inner
+
+    def decide(st, feat_prev):
+        go = d0(st, feat_prev)                            # (the wait counter runs on)
+        return go and not (feat_prev is not None and feat_prev[2] < min_ratio)
+    return decide, f0
+
+
 def clairvoyant():
     return "clairvoyant", None
 
@@ -62,6 +73,8 @@ POLICIES = {
     "spectrum tau<0.1 + exponential": spectrum(0.1, 1.0, backoff(1, [4, 8, 16])),
     "spectrum tau<0.05 + exponential": spectrum(0.05, 1.0, backoff(1, [4, 8, 16])),
     "spectrum tau<0.02 + no free retry 4,8,16": spectrum(0.02, 1.0, backoff(0, [4, 8, 16])),
+    "kept ratio >= 0.1 + exponential": graded(0.1, backoff(1, [4, 8, 16])),
+    "kept ratio >= 0.01 + exponential": graded(0.01, backoff(1, [4, 8, 16])),
     "clairvoyant (attempt iff accepted)": clairvoyant(),
     "never attempt": (lambda st, fp: False, lambda st, a: None),
 }
